@@ -1,0 +1,144 @@
+/* pbg.h -- C ABI of libpbg_b200.so: the B200 (sm_100a) replacement for the one hot path of
+ * Drjay806/PRO-B-GAN: the generator forward pass and the discriminator scoring pass that
+ * pro_b_gan_infer.py drives.  Citations are file:line into the reference.
+ *
+ * Conventions
+ *   - every function returns a pbg_status (0 = OK); no C++ exception crosses the ABI;
+ *     pbg_last_error() gives the message for the last non-zero status.
+ *   - all tensor pointers are DEVICE pointers on the ctx's device unless the name ends in
+ *     _host; buffers are caller-owned, row-major and contiguous; fp32 unless stated.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Device-pointer
+ *     entry points are stream-ordered and never synchronise; *_host entry points are
+ *     synchronous (H2D copy, kernels, D2H copy, one stream sync).
+ *   - a ctx is bound to one device and is not thread-safe (the reference is single
+ *     threaded and synchronous, pro_b_gan_infer.py:133-165).
+ *   - there is no CPU fallback: on a machine without an sm_100 device pbg_create fails.
+ */
+#ifndef PBG_H_
+#define PBG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBG_ABI_VERSION 1
+
+typedef struct pbg_ctx pbg_ctx;
+
+typedef enum pbg_status {
+  PBG_OK = 0,
+  PBG_ERR_INVALID = 1,     /* bad argument / shape                                        */
+  PBG_ERR_CUDA = 2,        /* a CUDA runtime or driver call failed                        */
+  PBG_ERR_NOT_LOADED = 3,  /* forward called before the matching pbg_load_*               */
+  PBG_ERR_INDEX = 4,       /* an entity / relation id was out of range (-> IndexError)    */
+  PBG_ERR_UNSUPPORTED = 5, /* no sm_100 device, or dims the kernels cannot tile           */
+  PBG_ERR_NOMEM = 6
+} pbg_status;
+
+/* arithmetic mode of the Linear layers */
+typedef enum pbg_precision {
+  PBG_PREC_F32 = 0,  /* SIMT FFMA, fp32 end to end: the parity mode (max-abs 1e-4)        */
+  PBG_PREC_BF16 = 1  /* tcgen05 kind::f16 (bf16 x bf16 -> fp32 in TMEM): the fast mode    */
+} pbg_precision;
+
+/* element type of the generator output buffer */
+typedef enum pbg_dtype { PBG_DT_F32 = 0, PBG_DT_BF16 = 1 } pbg_dtype;
+
+/* Model dimensions.  embed_dim / noise_dim / d_hidden are the checkpoint's args
+ * (pro_b_gan_infer.py:77-80); g_hidden is the generator's internal hidden width (the
+ * reference passes no hidden_dim to Generator, :93; the oracle default is 1024). */
+typedef struct pbg_dims {
+  int32_t embed_dim;  /* E */
+  int32_t noise_dim;  /* Z */
+  int32_t g_hidden;   /* generator: (2E+Z) -> g_hidden -> g_hidden -> E                   */
+  int32_t d_hidden;   /* discriminator: 3E -> d_hidden -> d_hidden/2 -> 1                 */
+  int32_t device;     /* CUDA device ordinal                                              */
+  float leaky_slope;  /* LeakyReLU negative slope (0.2)                                   */
+} pbg_dims;
+
+int pbg_abi_version(void);
+
+/* Replaces `Generator(E, Z).to(device)` / `Discriminator(E, H).to(device)`
+ * (pro_b_gan_infer.py:93-94): allocates the device-side state for one model pair. */
+int pbg_create(pbg_ctx** out, const pbg_dims* dims);
+void pbg_destroy(pbg_ctx* ctx);
+
+/* Message for the last failing call on ctx (ctx == NULL: last failing pbg_create). */
+const char* pbg_last_error(const pbg_ctx* ctx);
+
+/* Replaces `generator.load_state_dict(...)` + `.eval()` (pro_b_gan_infer.py:97, :106).
+ * `packed_host` is a HOST buffer of fp32 with eval-mode BatchNorm already folded into the
+ * preceding Linear by the host (legal because of :106 / torch.no_grad :133):
+ *   W1[g_hidden, 2E+Z] b1[g_hidden] W2[g_hidden, g_hidden] b2[g_hidden] W3[E, g_hidden] b3[E]
+ * (each W row-major [out, in], PyTorch's nn.Linear layout).  n_floats must match exactly. */
+int pbg_load_generator(pbg_ctx* ctx, const float* packed_host, size_t n_floats);
+
+/* Replaces `discriminator.load_state_dict(...)` + `.eval()` (pro_b_gan_infer.py:98, :107):
+ *   W1[H, 3E] b1[H] W2[H/2, H] b2[H/2] w3[H/2] b3[1] */
+int pbg_load_discriminator(pbg_ctx* ctx, const float* packed_host, size_t n_floats);
+
+/* Replaces `self.generator(h_emb, r_emb)` (pro_b_gan_infer.py:143, :201).
+ * h, r: [B,E] fp32; z: [B,Z] fp32 latents (the reference's forward takes no noise argument;
+ * the host module draws z from its seeded CPU generator and passes it here).
+ * out: [B,E] of `out_dtype`.  tanh output. */
+int pbg_generator_forward(pbg_ctx* ctx, const float* h, const float* r, const float* z, void* out,
+                          int64_t B, int precision, int out_dtype, void* stream);
+
+/* Replaces gather + forward: `h_emb = node_emb[heads]; r_emb = rel_emb(relations);
+ * generator(h_emb, r_emb)` (pro_b_gan_infer.py:139-143 and :186-187, :201).
+ * node_emb [N,E], rel_emb [R,E]; heads / rels are int64 with element strides (the
+ * reference's `triplet_tensor[:, i]` columns are stride-3 views, :183). */
+int pbg_generator_forward_gather(pbg_ctx* ctx, const float* node_emb, int64_t N, const float* rel_emb,
+                                 int64_t R, const int64_t* heads, int64_t head_stride,
+                                 const int64_t* rels, int64_t rel_stride, const float* z, void* out,
+                                 int64_t B, int precision, int out_dtype, void* stream);
+
+/* Replaces `self.discriminator(h_emb, r_emb, t_emb)` (pro_b_gan_infer.py:301) and the
+ * sigmoid that follows it (:302).  logits [B] fp32; probs [B] fp32 or NULL. */
+int pbg_discriminator_forward(pbg_ctx* ctx, const float* h, const float* r, const float* t,
+                              float* logits, float* probs, int64_t B, int precision, void* stream);
+
+/* Replaces `discriminator.score_triplets(node_emb, rel_emb, triplet_tensor)`
+ * (pro_b_gan_infer.py:207): triplets [B,3] int64 contiguous (head, relation, tail). */
+int pbg_discriminator_score_triplets(pbg_ctx* ctx, const float* node_emb, int64_t N,
+                                     const float* rel_emb, int64_t R, const int64_t* triplets,
+                                     float* logits, float* probs, int64_t B, int precision,
+                                     void* stream);
+
+/* The canonical generator+discriminator pass of `ProtBGANInference.score_triplets`
+ * (pro_b_gan_infer.py:186-188, :201-202, :207) in one call sharing one gather:
+ *   gen_out    [B,E] predicted tail embeddings (G.forward, :201), or NULL
+ *   gen_scores [B]   cosine_similarity(pred, node_emb[tail], dim=1) (:202), or NULL
+ *                    (both NULL: the generator is skipped)
+ *   logits / probs [B] discriminator logit and sigmoid(logit) (:207); NULL logits skips D.
+ * Needs the matching models loaded in this ctx. */
+int pbg_score_triplets(pbg_ctx* ctx, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                       const int64_t* triplets, const float* z, void* gen_out, int out_dtype,
+                       float* gen_scores, float* logits, float* probs, int64_t B, int precision,
+                       void* stream);
+
+/* Same pass with HOST index / latent / result buffers: the end-to-end form the reference's
+ * list API implies (H2D at :182, D2H at :203, :208-209).  node_emb / rel_emb stay device
+ * pointers (they are model state moved once at load, :83, :102).  Synchronous.  Returns
+ * PBG_ERR_INDEX if any id is out of range (results are then undefined). */
+int pbg_score_triplets_host(pbg_ctx* ctx, const float* node_emb, int64_t N, const float* rel_emb,
+                            int64_t R, const int64_t* triplets_host, const float* z_host,
+                            float* gen_out_host, float* gen_scores_host, float* logits_host,
+                            float* probs_host, int64_t B, int precision);
+
+/* Out-of-range ids never fault on the device: the gather clamps them and raises a flag.
+ * This synchronises `stream`, returns PBG_ERR_INDEX if the flag was raised since the last
+ * check (and clears it), else PBG_OK.  The Python host turns it into IndexError, the
+ * exception the reference's `node_emb[heads]` raises (pro_b_gan_infer.py:139). */
+int pbg_check_indices(pbg_ctx* ctx, void* stream);
+
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t pbg_launch_count(const pbg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBG_H_ */

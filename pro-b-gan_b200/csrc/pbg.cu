@@ -1,0 +1,550 @@
+// pbg.cu -- libpbg_b200.so: context, weight ingest, workspaces, TMA descriptors and the launch sequence behind
+// the C ABI declared in include/pbg.h.  Device code lives in gather.cuh / gemm_tc.cuh / gemm_f32.cuh.
+//
+// HBM layout per ctx (sized lazily to the largest batch chunk seen, <= kMaxChunk rows):
+//   weights   : fp32 [out,in] + bias (parity mode) and bf16 [out_p, in_p] zero-padded to the tile grid + padded bias
+//   bf16 mode : xg0 [rows, Kg0p]  xd0 [rows, Kd0p]  bufA [rows, Hmax]  bufB [rows, Hmax]   (bf16, K-major, the
+//               A operands of the next GEMM, each with a SWIZZLE_128B CUtensorMap of box 128 x 64)
+//   fp32 mode : the same four buffers in fp32
+// G: xg0 -> bufA -> bufB -> out.   D: xd0 -> bufA -> (logit, prob).   One stream at a time per ctx.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/pbg.h"
+#include "gather.cuh"
+#include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
+
+using namespace pbg;
+
+namespace {
+
+constexpr long long kMaxChunk = 65536;  // rows processed per launch sequence (bounds the workspaces)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Linear {
+  int n = 0, k = 0;    // logical [out, in]
+  int np = 0, kp = 0;  // padded to the tensor-core tile grid
+  int block_n = 0;
+  float* w_f32 = nullptr;
+  float* b_f32 = nullptr;
+  __nv_bfloat16* w_bf16 = nullptr;
+  float* b_pad = nullptr;
+  CUtensorMap tmap_w;
+};
+
+struct Workspace {
+  long long rows = 0;
+  void *xg0 = nullptr, *xd0 = nullptr, *bufA = nullptr, *bufB = nullptr;
+  CUtensorMap tm_xg0, tm_xd0, tm_bufA_g, tm_bufA_d, tm_bufB_g;
+};
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct pbg_ctx {
+  pbg_dims dims{};
+  int num_sms = 0;
+  bool g_loaded = false, d_loaded = false;
+  int kg0 = 0, kg0p = 0, kd0 = 0, kd0p = 0, hgp = 0, hdp = 0, hd2 = 0, hd2p = 0, ep = 0, hmax = 0;
+  Linear g[3], d[2];
+  float* d_w3 = nullptr;      // [hd2] fp32
+  float* d_w3_pad = nullptr;  // [hd2p]
+  float d_b3 = 0.f;
+  Workspace ws_bf16, ws_f32;
+  int* err_flag = nullptr;       // device
+  int* err_flag_host = nullptr;  // pinned
+  cudaStream_t own_stream = nullptr;
+  // device staging for the *_host entry point
+  long long host_cap = 0;
+  long long* st_trip = nullptr;
+  float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
+  EncodeTiledFn encode = nullptr;
+  long long launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(pbg_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define PBG_CUDA(c, expr)                                                                               \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) return fail((c), PBG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define PBG_TRY(expr)            \
+  do {                           \
+    int s_ = (expr);             \
+    if (s_ != PBG_OK) return s_; \
+  } while (0)
+
+int make_tmap(pbg_ctx* c, CUtensorMap* tm, const void* base, long long rows, int cols, int box_rows) {
+  // 2-D bf16 [rows, cols] row-major; box = box_rows x 64 elements (128 B inner = one swizzle row)
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, PBG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d", (int)r, rows, cols);
+  return PBG_OK;
+}
+
+void free_linear(Linear& l) {
+  cudaFree(l.w_f32); cudaFree(l.b_f32); cudaFree(l.w_bf16); cudaFree(l.b_pad);
+  l = Linear{};
+}
+
+void free_ws(Workspace& w) {
+  cudaFree(w.xg0); cudaFree(w.xd0); cudaFree(w.bufA); cudaFree(w.bufB);
+  w = Workspace{};
+}
+
+// Upload one Linear: fp32 copy for the parity mode, padded bf16 copy + TMA descriptor for the tensor-core mode.
+int upload_linear(pbg_ctx* c, Linear& l, int n, int k, int kp, const float* w_host, const float* b_host) {
+  free_linear(l);
+  l.n = n; l.k = k; l.kp = kp;
+  l.np = round_up(n, 128);
+  l.block_n = (l.np % 256 == 0) ? 256 : 128;
+  PBG_CUDA(c, cudaMalloc(&l.w_f32, sizeof(float) * n * k));
+  PBG_CUDA(c, cudaMalloc(&l.b_f32, sizeof(float) * n));
+  PBG_CUDA(c, cudaMalloc(&l.w_bf16, sizeof(__nv_bfloat16) * (size_t)l.np * l.kp));
+  PBG_CUDA(c, cudaMalloc(&l.b_pad, sizeof(float) * l.np));
+  PBG_CUDA(c, cudaMemcpyAsync(l.w_f32, w_host, sizeof(float) * n * k, cudaMemcpyHostToDevice, c->own_stream));
+  PBG_CUDA(c, cudaMemcpyAsync(l.b_f32, b_host, sizeof(float) * n, cudaMemcpyHostToDevice, c->own_stream));
+  pack_bf16_kernel<<<c->num_sms * 4, 256, 0, c->own_stream>>>(l.w_f32, l.w_bf16, n, k, l.np, l.kp);
+  pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(l.b_f32, l.b_pad, n, l.np);
+  c->launches += 2;
+  PBG_CUDA(c, cudaGetLastError());
+  PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
+  return make_tmap(c, &l.tmap_w, l.w_bf16, l.np, l.kp, l.block_n);
+}
+
+int ensure_ws(pbg_ctx* c, int prec, long long rows) {
+  Workspace& w = prec == PBG_PREC_BF16 ? c->ws_bf16 : c->ws_f32;
+  if (w.rows >= rows) return PBG_OK;
+  // round the capacity up so that small calls do not keep reallocating
+  long long cap = 1024;
+  while (cap < rows) cap *= 2;
+  cap = std::min(cap, kMaxChunk);
+  PBG_CUDA(c, cudaDeviceSynchronize());  // nothing may still be reading the old buffers
+  free_ws(w);
+  if (prec == PBG_PREC_BF16) {
+    const size_t es = sizeof(__nv_bfloat16);
+    PBG_CUDA(c, cudaMalloc(&w.xg0, es * cap * c->kg0p));
+    PBG_CUDA(c, cudaMalloc(&w.xd0, es * cap * c->kd0p));
+    PBG_CUDA(c, cudaMalloc(&w.bufA, es * cap * c->hmax));
+    PBG_CUDA(c, cudaMalloc(&w.bufB, es * cap * c->hmax));
+    PBG_TRY(make_tmap(c, &w.tm_xg0, w.xg0, cap, c->kg0p, kBlockM));
+    PBG_TRY(make_tmap(c, &w.tm_xd0, w.xd0, cap, c->kd0p, kBlockM));
+    PBG_TRY(make_tmap(c, &w.tm_bufA_g, w.bufA, cap, c->hgp, kBlockM));
+    PBG_TRY(make_tmap(c, &w.tm_bufA_d, w.bufA, cap, c->hdp, kBlockM));
+    PBG_TRY(make_tmap(c, &w.tm_bufB_g, w.bufB, cap, c->hgp, kBlockM));
+  } else {
+    const size_t es = sizeof(float);
+    const int hm = std::max(std::max(c->dims.g_hidden, c->dims.d_hidden), c->dims.embed_dim);
+    PBG_CUDA(c, cudaMalloc(&w.xg0, es * cap * c->kg0));
+    PBG_CUDA(c, cudaMalloc(&w.xd0, es * cap * c->kd0));
+    PBG_CUDA(c, cudaMalloc(&w.bufA, es * cap * hm));
+    PBG_CUDA(c, cudaMalloc(&w.bufB, es * cap * hm));
+  }
+  w.rows = cap;
+  return PBG_OK;
+}
+
+template <int BLOCK_N, int STAGES, int EPI>
+int launch_gemm_inst(pbg_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+  using L = GemmSmem<BLOCK_N, STAGES>;
+  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, EPI>;
+  static bool attr_set = false;  // per instantiation; ctxs on different devices share the function handle
+  static int attr_dev = -1;
+  if (!attr_set || attr_dev != c->dims.device) {
+    PBG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true; attr_dev = c->dims.device;
+  }
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int items = (EPI == EPI_LEAKY) ? m_tiles * (p.N / BLOCK_N) : m_tiles;
+  const int grid = std::max(1, std::min(items, c->num_sms));
+  kern<<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, p);
+  c->launches += 1;
+  PBG_CUDA(c, cudaGetLastError());
+  return PBG_OK;
+}
+
+template <int EPI>
+int launch_gemm(pbg_ctx* c, const Linear& l, const CUtensorMap& ta, GemmParams p, cudaStream_t s) {
+  p.N = l.np; p.K = l.kp; p.bias = l.b_pad; p.slope = c->dims.leaky_slope;
+  if (l.block_n == 256) return launch_gemm_inst<256, 4, EPI>(c, ta, l.tmap_w, p, s);
+  return launch_gemm_inst<128, 6, EPI>(c, ta, l.tmap_w, p, s);
+}
+
+template <int ACT>
+int launch_f32(pbg_ctx* c, const Linear& l, const float* A, long long lda, float* out, long long ldo, long long M,
+               cudaStream_t s) {
+  F32GemmParams p{A, lda, l.w_f32, l.k, l.b_f32, out, ldo, (int)M, l.n, l.k, c->dims.leaky_slope};
+  dim3 grid((l.n + 63) / 64, (unsigned)((M + 63) / 64));
+  gemm_f32_kernel<ACT><<<grid, 256, 0, s>>>(p);
+  c->launches += 1;
+  PBG_CUDA(c, cudaGetLastError());
+  return PBG_OK;
+}
+
+struct Pass {
+  const float* node_emb = nullptr; long long N = 0;
+  const float* rel_emb = nullptr;  long long R = 0;
+  const long long *heads = nullptr, *rels = nullptr, *tails = nullptr;
+  long long hs = 1, rs = 1, ts = 1;
+  const float *h = nullptr, *r = nullptr, *t = nullptr, *z = nullptr;
+  void* gen_out = nullptr; int out_dtype = PBG_DT_F32;
+  float *gen_scores = nullptr, *logits = nullptr, *probs = nullptr;
+  bool run_g = false, run_d = false;
+  long long B = 0; int prec = PBG_PREC_BF16; cudaStream_t stream = nullptr;
+};
+
+int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
+  const int E = c->dims.embed_dim, Z = c->dims.noise_dim;
+  const bool bf = a.prec == PBG_PREC_BF16;
+  Workspace& w = bf ? c->ws_bf16 : c->ws_f32;
+  cudaStream_t s = a.stream;
+
+  GatherParams gp{};
+  gp.node_emb = a.node_emb; gp.rel_emb = a.rel_emb; gp.N = a.N; gp.R = a.R; gp.E = E; gp.Z = Z;
+  gp.heads = a.heads ? a.heads + off * a.hs : nullptr; gp.head_stride = a.hs;
+  gp.rels = a.rels ? a.rels + off * a.rs : nullptr;    gp.rel_stride = a.rs;
+  gp.tails = a.tails ? a.tails + off * a.ts : nullptr; gp.tail_stride = a.ts;
+  gp.h = a.h ? a.h + off * E : nullptr; gp.r = a.r ? a.r + off * E : nullptr; gp.t = a.t ? a.t + off * E : nullptr;
+  gp.z = a.z ? a.z + off * Z : nullptr;
+  gp.xg = a.run_g ? w.xg0 : nullptr; gp.ldg = bf ? c->kg0p : c->kg0;
+  gp.xd = a.run_d ? w.xd0 : nullptr; gp.ldd = bf ? c->kd0p : c->kd0;
+  gp.B = rows; gp.err_flag = c->err_flag;
+  const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
+  if (bf) gather_concat_kernel<__nv_bfloat16><<<gather_blocks, 256, 0, s>>>(gp);
+  else    gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp);
+  c->launches += 1;
+  PBG_CUDA(c, cudaGetLastError());
+
+  const size_t out_es = a.out_dtype == PBG_DT_BF16 ? 2 : 4;
+  void* gen_out = a.gen_out ? static_cast<char*>(a.gen_out) + (size_t)off * E * out_es : nullptr;
+  float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
+
+  if (bf) {
+    if (a.run_g) {
+      GemmParams p{};
+      p.M = (int)rows;
+      p.out = w.bufA; p.ldo = c->hgp; p.n_valid = c->hgp;
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->g[0], w.tm_xg0, p, s));
+      p.out = w.bufB;
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->g[1], w.tm_bufA_g, p, s));
+      GemmParams q{};
+      q.M = (int)rows; q.out = gen_out; q.ldo = E; q.n_valid = E; q.out_f32 = a.out_dtype == PBG_DT_F32;
+      if (scores) {
+        q.cosine = scores; q.tail_tab = a.node_emb; q.n_ent = a.N;
+        q.tail_idx = a.tails + off * a.ts; q.tail_stride = a.ts;
+      }
+      PBG_TRY(launch_gemm<EPI_TANH>(c, c->g[2], w.tm_bufB_g, q, s));
+    }
+    if (a.run_d) {
+      GemmParams p{};
+      p.M = (int)rows; p.out = w.bufA; p.ldo = c->hdp; p.n_valid = c->hdp;
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->d[0], w.tm_xd0, p, s));
+      GemmParams q{};
+      q.M = (int)rows; q.w3 = c->d_w3_pad; q.b3 = c->d_b3; q.logits = a.logits + off;
+      q.probs = a.probs ? a.probs + off : nullptr;
+      PBG_TRY(launch_gemm<EPI_ROWDOT>(c, c->d[1], w.tm_bufA_d, q, s));
+    }
+  } else {
+    float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
+    const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
+    if (a.run_g) {
+      const int H = c->dims.g_hidden;
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->g[0], xg0, c->kg0, bufA, H, rows, s));
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->g[1], bufA, H, bufB, H, rows, s));
+      float* pred = gen_out ? (float*)gen_out : bufA;  // bufA is free once layer 2 has consumed it
+      PBG_TRY(launch_f32<ACT_TANH>(c, c->g[2], bufB, H, pred, E, rows, s));
+      if (scores) {
+        cosine_f32_kernel<<<row_blocks, 256, 0, s>>>(pred, E, a.node_emb, a.N, a.tails + off * a.ts, a.ts, E, rows,
+                                                     scores);
+        c->launches += 1;
+        PBG_CUDA(c, cudaGetLastError());
+      }
+    }
+    if (a.run_d) {
+      const int H = c->dims.d_hidden, H2 = c->hd2;
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->d[0], xd0, c->kd0, bufA, H, rows, s));
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->d[1], bufA, H, bufB, H2, rows, s));
+      rowdot_f32_kernel<<<row_blocks, 256, 0, s>>>(bufB, H2, c->d_w3, c->d_b3, H2, rows, a.logits + off,
+                                                   a.probs ? a.probs + off : nullptr);
+      c->launches += 1;
+      PBG_CUDA(c, cudaGetLastError());
+    }
+  }
+  return PBG_OK;
+}
+
+int run_pass(pbg_ctx* c, const Pass& a) {
+  if (!c) return PBG_ERR_INVALID;
+  if (a.B < 0) return fail(c, PBG_ERR_INVALID, "negative batch");
+  if (a.prec != PBG_PREC_F32 && a.prec != PBG_PREC_BF16) return fail(c, PBG_ERR_INVALID, "unknown precision %d", a.prec);
+  if (a.run_g && !c->g_loaded) return fail(c, PBG_ERR_NOT_LOADED, "generator weights not loaded");
+  if (a.run_d && !c->d_loaded) return fail(c, PBG_ERR_NOT_LOADED, "discriminator weights not loaded");
+  if (a.run_g && a.z == nullptr) return fail(c, PBG_ERR_INVALID, "generator needs latents z");
+  if (a.run_g && a.gen_out && a.prec == PBG_PREC_F32 && a.out_dtype != PBG_DT_F32)
+    return fail(c, PBG_ERR_INVALID, "fp32 mode writes fp32 output");
+  if (a.gen_scores && a.tails == nullptr) return fail(c, PBG_ERR_INVALID, "gen_scores needs tail ids");
+  if (a.B == 0 || (!a.run_g && !a.run_d)) return PBG_OK;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  const long long chunk = std::min(a.B, kMaxChunk);
+  PBG_TRY(ensure_ws(c, a.prec, chunk));
+  for (long long off = 0; off < a.B; off += chunk) PBG_TRY(run_chunk(c, a, off, std::min(chunk, a.B - off)));
+  return PBG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pbg_abi_version(void) { return PBG_ABI_VERSION; }
+
+const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
+  if (!out || !dims) return fail(nullptr, PBG_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const int E = dims->embed_dim, Z = dims->noise_dim, HG = dims->g_hidden, HD = dims->d_hidden;
+  if (E <= 0 || Z <= 0 || HG <= 0 || HD <= 0) return fail(nullptr, PBG_ERR_INVALID, "dims must be positive");
+  if (E % 8 || Z % 8 || HG % 8 || HD % 16)
+    return fail(nullptr, PBG_ERR_UNSUPPORTED, "embed_dim, noise_dim, g_hidden must be multiples of 8 and d_hidden of 16");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, PBG_ERR_UNSUPPORTED, "no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (dims->device < 0 || dims->device >= ndev) return fail(nullptr, PBG_ERR_INVALID, "device %d out of range", dims->device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, dims->device)) != cudaSuccess)
+    return fail(nullptr, PBG_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, PBG_ERR_UNSUPPORTED, "device %d is sm_%d%d; the kernels are sm_100a only (no fallback)",
+                dims->device, prop.major, prop.minor);
+  pbg_ctx* c = new (std::nothrow) pbg_ctx();
+  if (!c) return fail(nullptr, PBG_ERR_NOMEM, "out of host memory");
+  c->dims = *dims;
+  c->num_sms = prop.multiProcessorCount;
+  c->kg0 = 2 * E + Z; c->kg0p = round_up(c->kg0, kBlockK);
+  c->kd0 = 3 * E;     c->kd0p = round_up(c->kd0, kBlockK);
+  c->hgp = round_up(HG, 128); c->hdp = round_up(HD, 128);
+  c->hd2 = HD / 2; c->hd2p = round_up(c->hd2, 128);
+  c->ep = round_up(E, 128);
+  c->hmax = std::max(c->hgp, c->hdp);
+  auto bail = [&](int code) { g_create_error = c->err; pbg_destroy(c); return code; };
+  if (cudaSetDevice(dims->device) != cudaSuccess) { c->err = "cudaSetDevice failed"; return bail(PBG_ERR_CUDA); }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    c->err = "cuTensorMapEncodeTiled not available from the driver";
+    return bail(PBG_ERR_CUDA);
+  }
+  c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&c->err_flag, sizeof(int)) != cudaSuccess ||
+      cudaMemset(c->err_flag, 0, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost(&c->err_flag_host, sizeof(int)) != cudaSuccess) {
+    c->err = std::string("ctx allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+    return bail(PBG_ERR_CUDA);
+  }
+  *c->err_flag_host = 0;
+  *out = c;
+  return PBG_OK;
+}
+
+void pbg_destroy(pbg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->dims.device);
+  cudaDeviceSynchronize();
+  for (auto& l : c->g) free_linear(l);
+  for (auto& l : c->d) free_linear(l);
+  cudaFree(c->d_w3); cudaFree(c->d_w3_pad);
+  free_ws(c->ws_bf16); free_ws(c->ws_f32);
+  cudaFree(c->err_flag);
+  if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
+  cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
+  cudaFree(c->st_logits); cudaFree(c->st_probs);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+int pbg_load_generator(pbg_ctx* c, const float* p, size_t n_floats) {
+  if (!c || !p) return PBG_ERR_INVALID;
+  const size_t E = c->dims.embed_dim, H = c->dims.g_hidden, K0 = c->kg0;
+  const size_t want = H * K0 + H + H * H + H + E * H + E;
+  if (n_floats != want) return fail(c, PBG_ERR_INVALID, "generator blob has %zu floats, expected %zu", n_floats, want);
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  c->g_loaded = false;
+  const float* w1 = p;            const float* b1 = w1 + H * K0;
+  const float* w2 = b1 + H;       const float* b2 = w2 + H * H;
+  const float* w3 = b2 + H;       const float* b3 = w3 + E * H;
+  PBG_TRY(upload_linear(c, c->g[0], (int)H, (int)K0, c->kg0p, w1, b1));
+  PBG_TRY(upload_linear(c, c->g[1], (int)H, (int)H, c->hgp, w2, b2));
+  PBG_TRY(upload_linear(c, c->g[2], (int)E, (int)H, c->hgp, w3, b3));
+  c->g_loaded = true;
+  return PBG_OK;
+}
+
+int pbg_load_discriminator(pbg_ctx* c, const float* p, size_t n_floats) {
+  if (!c || !p) return PBG_ERR_INVALID;
+  const size_t H = c->dims.d_hidden, H2 = c->hd2, K0 = c->kd0;
+  const size_t want = H * K0 + H + H2 * H + H2 + H2 + 1;
+  if (n_floats != want) return fail(c, PBG_ERR_INVALID, "discriminator blob has %zu floats, expected %zu", n_floats, want);
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  c->d_loaded = false;
+  const float* w1 = p;            const float* b1 = w1 + H * K0;
+  const float* w2 = b1 + H;       const float* b2 = w2 + H2 * H;
+  const float* w3 = b2 + H2;      const float* b3 = w3 + H2;
+  PBG_TRY(upload_linear(c, c->d[0], (int)H, (int)K0, c->kd0p, w1, b1));
+  PBG_TRY(upload_linear(c, c->d[1], (int)H2, (int)H, c->hdp, w2, b2));
+  cudaFree(c->d_w3); cudaFree(c->d_w3_pad); c->d_w3 = c->d_w3_pad = nullptr;
+  const int np = c->d[1].np;  // the row-dot walks the padded width of layer 2
+  PBG_CUDA(c, cudaMalloc(&c->d_w3, sizeof(float) * H2));
+  PBG_CUDA(c, cudaMalloc(&c->d_w3_pad, sizeof(float) * np));
+  PBG_CUDA(c, cudaMemcpyAsync(c->d_w3, w3, sizeof(float) * H2, cudaMemcpyHostToDevice, c->own_stream));
+  pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(c->d_w3, c->d_w3_pad, (int)H2, np);
+  c->launches += 1;
+  PBG_CUDA(c, cudaGetLastError());
+  PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
+  c->d_b3 = *b3;
+  c->d_loaded = true;
+  return PBG_OK;
+}
+
+int pbg_generator_forward(pbg_ctx* c, const float* h, const float* r, const float* z, void* out, int64_t B,
+                          int precision, int out_dtype, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B > 0 && (!h || !r || !out)) return fail(c, PBG_ERR_INVALID, "null tensor");
+  Pass a; a.h = h; a.r = r; a.z = z; a.gen_out = out; a.out_dtype = out_dtype; a.run_g = true;
+  a.B = B; a.prec = precision; a.stream = (cudaStream_t)stream;
+  return run_pass(c, a);
+}
+
+int pbg_generator_forward_gather(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                                 const int64_t* heads, int64_t head_stride, const int64_t* rels, int64_t rel_stride,
+                                 const float* z, void* out, int64_t B, int precision, int out_dtype, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B > 0 && (!node_emb || !rel_emb || !heads || !rels || !out)) return fail(c, PBG_ERR_INVALID, "null tensor");
+  Pass a; a.node_emb = node_emb; a.N = N; a.rel_emb = rel_emb; a.R = R;
+  a.heads = (const long long*)heads; a.hs = head_stride; a.rels = (const long long*)rels; a.rs = rel_stride;
+  a.z = z; a.gen_out = out; a.out_dtype = out_dtype; a.run_g = true;
+  a.B = B; a.prec = precision; a.stream = (cudaStream_t)stream;
+  return run_pass(c, a);
+}
+
+int pbg_discriminator_forward(pbg_ctx* c, const float* h, const float* r, const float* t, float* logits, float* probs,
+                              int64_t B, int precision, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B > 0 && (!h || !r || !t || !logits)) return fail(c, PBG_ERR_INVALID, "null tensor");
+  Pass a; a.h = h; a.r = r; a.t = t; a.logits = logits; a.probs = probs; a.run_d = true;
+  a.B = B; a.prec = precision; a.stream = (cudaStream_t)stream;
+  return run_pass(c, a);
+}
+
+int pbg_discriminator_score_triplets(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                                     const int64_t* triplets, float* logits, float* probs, int64_t B, int precision,
+                                     void* stream) {
+  return pbg_score_triplets(c, node_emb, N, rel_emb, R, triplets, nullptr, nullptr, PBG_DT_F32, nullptr, logits, probs,
+                            B, precision, stream);
+}
+
+int pbg_score_triplets(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                       const int64_t* triplets, const float* z, void* gen_out, int out_dtype, float* gen_scores,
+                       float* logits, float* probs, int64_t B, int precision, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B > 0 && (!node_emb || !rel_emb || !triplets)) return fail(c, PBG_ERR_INVALID, "null tensor");
+  Pass a; a.node_emb = node_emb; a.N = N; a.rel_emb = rel_emb; a.R = R;
+  const long long* t = (const long long*)triplets;
+  a.heads = t; a.rels = t + 1; a.tails = t + 2; a.hs = a.rs = a.ts = 3;
+  a.z = z; a.gen_out = gen_out; a.out_dtype = out_dtype; a.gen_scores = gen_scores;
+  a.logits = logits; a.probs = probs;
+  a.run_g = (gen_out != nullptr || gen_scores != nullptr); a.run_d = (logits != nullptr);
+  a.B = B; a.prec = precision; a.stream = (cudaStream_t)stream;
+  return run_pass(c, a);
+}
+
+int pbg_check_indices(pbg_ctx* c, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  PBG_CUDA(c, cudaMemcpyAsync(c->err_flag_host, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PBG_CUDA(c, cudaStreamSynchronize(s));
+  if (*c->err_flag_host != 0) {
+    PBG_CUDA(c, cudaMemsetAsync(c->err_flag, 0, sizeof(int), s));
+    PBG_CUDA(c, cudaStreamSynchronize(s));
+    return fail(c, PBG_ERR_INDEX, "index out of range in embedding gather");
+  }
+  return PBG_OK;
+}
+
+int pbg_score_triplets_host(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                            const int64_t* triplets_host, const float* z_host, float* gen_out_host,
+                            float* gen_scores_host, float* logits_host, float* probs_host, int64_t B, int precision) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B < 0) return fail(c, PBG_ERR_INVALID, "negative batch");
+  if (B == 0) return PBG_OK;
+  if (!triplets_host) return fail(c, PBG_ERR_INVALID, "null triplets");
+  const bool run_g = gen_out_host || gen_scores_host;
+  if (run_g && !z_host) return fail(c, PBG_ERR_INVALID, "generator needs latents z");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  const int E = c->dims.embed_dim, Z = c->dims.noise_dim;
+  if (c->host_cap < B) {
+    PBG_CUDA(c, cudaDeviceSynchronize());
+    cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
+    cudaFree(c->st_logits); cudaFree(c->st_probs);
+    c->st_trip = nullptr; c->st_z = c->st_gen = c->st_scores = c->st_logits = c->st_probs = nullptr;
+    c->host_cap = 0;
+    PBG_CUDA(c, cudaMalloc(&c->st_trip, sizeof(long long) * 3 * B));
+    PBG_CUDA(c, cudaMalloc(&c->st_z, sizeof(float) * Z * B));
+    PBG_CUDA(c, cudaMalloc(&c->st_gen, sizeof(float) * E * B));
+    PBG_CUDA(c, cudaMalloc(&c->st_scores, sizeof(float) * B));
+    PBG_CUDA(c, cudaMalloc(&c->st_logits, sizeof(float) * B));
+    PBG_CUDA(c, cudaMalloc(&c->st_probs, sizeof(float) * B));
+    c->host_cap = B;
+  }
+  cudaStream_t s = c->own_stream;
+  PBG_CUDA(c, cudaMemcpyAsync(c->st_trip, triplets_host, sizeof(long long) * 3 * B, cudaMemcpyHostToDevice, s));
+  if (run_g) PBG_CUDA(c, cudaMemcpyAsync(c->st_z, z_host, sizeof(float) * Z * B, cudaMemcpyHostToDevice, s));
+  PBG_TRY(pbg_score_triplets(c, node_emb, N, rel_emb, R, (const int64_t*)c->st_trip, run_g ? c->st_z : nullptr,
+                             gen_out_host ? c->st_gen : nullptr, PBG_DT_F32, gen_scores_host ? c->st_scores : nullptr,
+                             logits_host ? c->st_logits : nullptr, probs_host ? c->st_probs : nullptr, B, precision, s));
+  if (gen_out_host) PBG_CUDA(c, cudaMemcpyAsync(gen_out_host, c->st_gen, sizeof(float) * E * B, cudaMemcpyDeviceToHost, s));
+  if (gen_scores_host) PBG_CUDA(c, cudaMemcpyAsync(gen_scores_host, c->st_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+  if (logits_host) PBG_CUDA(c, cudaMemcpyAsync(logits_host, c->st_logits, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+  if (probs_host) PBG_CUDA(c, cudaMemcpyAsync(probs_host, c->st_probs, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+  return pbg_check_indices(c, s);  // one sync: results + the out-of-range flag
+}
+
+}  // extern "C"

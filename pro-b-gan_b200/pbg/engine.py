@@ -1,0 +1,209 @@
+"""Torch-tensor front end of the C ABI: one ``Engine`` = one ``pbg_ctx`` on one CUDA device.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libpbg_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from . import cabi
+
+_PRECISIONS = {"fp32": cabi.PREC_F32, "f32": cabi.PREC_F32, "float32": cabi.PREC_F32,
+               "bf16": cabi.PREC_BF16, "bfloat16": cabi.PREC_BF16}
+
+
+def default_precision() -> str:
+    """``PBG_PRECISION`` env var (``bf16`` = tcgen05 fast mode, default; ``fp32`` = parity mode).
+
+    An env var rather than a CLI flag so the reference's argparse surface stays untouched."""
+    return os.environ.get("PBG_PRECISION", "bf16").lower()
+
+
+def precision_code(precision: str | None) -> int:
+    p = (precision or default_precision()).lower()
+    if p not in _PRECISIONS:
+        raise ValueError(f"unknown precision {p!r}; use 'fp32' or 'bf16'")
+    return _PRECISIONS[p]
+
+
+def fold_linear_bn(lin: nn.Linear, bn: nn.BatchNorm1d | None):
+    """Fold an eval-mode BatchNorm1d into the preceding Linear (float64 arithmetic, fp32 result).
+
+    Legal because the reference only runs the modules in eval mode under no_grad
+    (pro_b_gan_infer.py:106-107, :133)."""
+    W = lin.weight.detach().double().cpu()
+    b = lin.bias.detach().double().cpu() if lin.bias is not None else torch.zeros(W.shape[0], dtype=torch.float64)
+    if bn is not None:
+        s = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+        W = W * s[:, None]
+        b = (b - bn.running_mean.detach().double().cpu()) * s + bn.bias.detach().double().cpu()
+    return W.float().contiguous(), b.float().contiguous()
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class Engine:
+    """Owns a pbg_ctx.  Methods take / return CUDA tensors on the engine's device."""
+
+    def __init__(self, embed_dim: int, noise_dim: int, g_hidden: int, d_hidden: int,
+                 device: torch.device | str | int, leaky_slope: float = 0.2):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"pro-b-gan_b200 runs only on CUDA (sm_100a) devices, got {device}; there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise RuntimeError("pro-b-gan_b200: no CUDA device is available and there is no CPU fallback")
+        self.device = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        self.E, self.Z, self.HG, self.HD = int(embed_dim), int(noise_dim), int(g_hidden), int(d_hidden)
+        self._lib = cabi.load()
+        self._h = C.c_void_p(0)
+        dims = cabi.PbgDims(self.E, self.Z, self.HG, self.HD, self.device.index, float(leaky_slope))
+        st = self._lib.pbg_create(C.byref(self._h), C.byref(dims))
+        if st != cabi.PBG_OK:
+            self._h = C.c_void_p(0)
+            cabi.check(st, None)
+        self.g_loaded = self.d_loaded = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.pbg_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p(0)
+
+    # ------------------------------------------------------------------ weights
+    def load_generator(self, layers) -> None:
+        """layers: [(W1,b1),(W2,b2),(W3,b3)] fp32 CPU tensors, BatchNorm already folded."""
+        blob = torch.cat([t.reshape(-1).float().cpu() for wb in layers for t in wb]).contiguous()
+        cabi.check(self._lib.pbg_load_generator(self._h, C.c_void_p(blob.data_ptr()), blob.numel()), self._h)
+        self.g_loaded = True
+
+    def load_discriminator(self, layers) -> None:
+        """layers: [(W1,b1),(W2,b2),(w3,b3)] fp32 CPU tensors."""
+        blob = torch.cat([t.reshape(-1).float().cpu() for wb in layers for t in wb]).contiguous()
+        cabi.check(self._lib.pbg_load_discriminator(self._h, C.c_void_p(blob.data_ptr()), blob.numel()), self._h)
+        self.d_loaded = True
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t: torch.Tensor, cols: int, name: str) -> torch.Tensor:
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, engine is on {self.device}")
+        if t.dim() != 2 or t.shape[1] != cols:
+            raise ValueError(f"{name} must be [B, {cols}], got {tuple(t.shape)}")
+        return t.detach().to(torch.float32).contiguous()
+
+    def _i64(self, t: torch.Tensor, name: str) -> torch.Tensor:
+        if t.device != self.device:
+            raise RuntimeError(f"{name} is on {t.device}, engine is on {self.device}")
+        return t.detach().to(torch.int64)
+
+    def check_indices(self) -> None:
+        """Synchronise and raise IndexError if a gather since the last check saw an out-of-range id."""
+        cabi.check(self._lib.pbg_check_indices(self._h, self._stream()), self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pbg_launch_count(self._h))
+
+    # ------------------------------------------------------------------ generator
+    def generator_forward(self, h, r, z, precision=None, out_dtype=torch.float32) -> torch.Tensor:
+        h, r, z = self._f32(h, self.E, "h_emb"), self._f32(r, self.E, "r_emb"), self._f32(z, self.Z, "z")
+        B = h.shape[0]
+        if r.shape[0] != B or z.shape[0] != B:
+            raise ValueError("h_emb, r_emb and z must have the same batch size")
+        out = torch.empty(B, self.E, dtype=out_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_generator_forward(
+                self._h, _ptr(h), _ptr(r), _ptr(z), _ptr(out), B, precision_code(precision),
+                cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32, self._stream()), self._h)
+        return out
+
+    def generator_forward_gather(self, node_emb, rel_w, heads, rels, z, precision=None,
+                                 out_dtype=torch.float32) -> torch.Tensor:
+        node_emb = self._f32(node_emb, self.E, "node_emb")
+        rel_w = self._f32(rel_w, self.E, "rel_emb.weight")
+        heads, rels = self._i64(heads, "heads"), self._i64(rels, "relations")
+        z = self._f32(z, self.Z, "z")
+        B = heads.shape[0]
+        out = torch.empty(B, self.E, dtype=out_dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_generator_forward_gather(
+                self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0],
+                _ptr(heads), heads.stride(0) if B else 1, _ptr(rels), rels.stride(0) if B else 1, _ptr(z), _ptr(out),
+                B, precision_code(precision), cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32,
+                self._stream()), self._h)
+        return out
+
+    # ------------------------------------------------------------------ discriminator
+    def discriminator_forward(self, h, r, t, precision=None):
+        h, r, t = self._f32(h, self.E, "h_emb"), self._f32(r, self.E, "r_emb"), self._f32(t, self.E, "t_emb")
+        B = h.shape[0]
+        logits = torch.empty(B, dtype=torch.float32, device=self.device)
+        probs = torch.empty(B, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_discriminator_forward(
+                self._h, _ptr(h), _ptr(r), _ptr(t), _ptr(logits), _ptr(probs), B, precision_code(precision),
+                self._stream()), self._h)
+        return logits, probs
+
+    # ------------------------------------------------------------------ fused G + D pass
+    def score_triplets(self, node_emb, rel_w, triplets, z=None, want_gen_out=False, want_gen_scores=False,
+                       want_disc=True, precision=None, out_dtype=torch.float32):
+        """One gather feeding G and/or D.  Returns dict with the requested tensors."""
+        node_emb = self._f32(node_emb, self.E, "node_emb")
+        rel_w = self._f32(rel_w, self.E, "rel_emb.weight")
+        trip = self._i64(triplets, "triplets")
+        if trip.dim() != 2 or trip.shape[1] != 3:
+            raise ValueError(f"triplets must be [B, 3], got {tuple(trip.shape)}")
+        trip = trip.contiguous()
+        B = trip.shape[0]
+        run_g = want_gen_out or want_gen_scores
+        if run_g:
+            if z is None:
+                raise ValueError("generator pass needs latents z")
+            z = self._f32(z, self.Z, "z")
+        res = {}
+        gen_out = torch.empty(B, self.E, dtype=out_dtype, device=self.device) if want_gen_out else None
+        scores = torch.empty(B, dtype=torch.float32, device=self.device) if want_gen_scores else None
+        logits = torch.empty(B, dtype=torch.float32, device=self.device) if want_disc else None
+        probs = torch.empty(B, dtype=torch.float32, device=self.device) if want_disc else None
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_score_triplets(
+                self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(trip),
+                _ptr(z if run_g else None), _ptr(gen_out),
+                cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32,
+                _ptr(scores), _ptr(logits), _ptr(probs), B, precision_code(precision), self._stream()), self._h)
+        if want_gen_out:
+            res["gen_out"] = gen_out
+        if want_gen_scores:
+            res["gen_scores"] = scores
+        if want_disc:
+            res["logits"], res["probs"] = logits, probs
+        return res
+
+    def score_triplets_host(self, node_emb, rel_w, triplets_host, z_host=None, gen_out_host=None,
+                            gen_scores_host=None, logits_host=None, probs_host=None, precision=None) -> None:
+        """End-to-end form: index / latent / result buffers are HOST tensors (ideally pinned); the H2D and
+        D2H copies happen inside the call, which returns after one stream synchronise."""
+        for name, t in (("triplets", triplets_host), ("z", z_host), ("gen_out", gen_out_host),
+                        ("gen_scores", gen_scores_host), ("logits", logits_host), ("probs", probs_host)):
+            if t is not None and (t.device.type != "cpu" or not t.is_contiguous()):
+                raise ValueError(f"{name}_host must be a contiguous CPU tensor")
+        if triplets_host.dtype != torch.int64 or triplets_host.dim() != 2 or triplets_host.shape[1] != 3:
+            raise ValueError("triplets_host must be int64 [B, 3]")
+        B = triplets_host.shape[0]
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_score_triplets_host(
+                self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(triplets_host),
+                _ptr(z_host), _ptr(gen_out_host), _ptr(gen_scores_host), _ptr(logits_host), _ptr(probs_host),
+                B, precision_code(precision)), self._h)
