@@ -135,6 +135,16 @@ int pbg_score_triplets_host(pbg_ctx* ctx, const float* node_emb, int64_t N, cons
  * exception the reference's `node_emb[heads]` raises (pro_b_gan_infer.py:139). */
 int pbg_check_indices(pbg_ctx* ctx, void* stream);
 
+/* Diagnostics / per-layer known-answer tests: run ONE Linear layer of a loaded model on the
+ * tensor cores.  model 0 = generator (layers 0..2), 1 = discriminator (layers 0..1; layer 1
+ * includes the folded final H/2 -> 1 dot product).  a_bf16 is a device [M, Kp] bf16 matrix
+ * (Kp = the layer's input width rounded up to 64).  out is
+ *   bf16 [M, Np]  for the LeakyReLU layers (Np = output width rounded up to 128),
+ *   fp32 [M, E]   for generator layer 2 (tanh),
+ *   fp32 [M]      for discriminator layer 1 (logits). */
+int pbg_linear_bf16(pbg_ctx* ctx, int model, int layer, const void* a_bf16, void* out, int64_t M,
+                    void* stream);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

@@ -495,6 +495,30 @@ int pbg_score_triplets(pbg_ctx* c, const float* node_emb, int64_t N, const float
   return run_pass(c, a);
 }
 
+int pbg_linear_bf16(pbg_ctx* c, int model, int layer, const void* a, void* out, int64_t M, void* stream) {
+  if (!c || !a || !out || M <= 0) return c ? fail(c, PBG_ERR_INVALID, "bad argument") : PBG_ERR_INVALID;
+  if (model == 0 && !c->g_loaded) return fail(c, PBG_ERR_NOT_LOADED, "generator weights not loaded");
+  if (model == 1 && !c->d_loaded) return fail(c, PBG_ERR_NOT_LOADED, "discriminator weights not loaded");
+  if (model < 0 || model > 1 || layer < 0 || layer > (model == 0 ? 2 : 1)) return fail(c, PBG_ERR_INVALID, "no such layer");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  const Linear& l = model == 0 ? c->g[layer] : c->d[layer];
+  CUtensorMap ta;
+  PBG_TRY(make_tmap(c, &ta, a, M, l.kp, kBlockM));
+  cudaStream_t s = (cudaStream_t)stream;
+  GemmParams p{};
+  p.M = (int)M;
+  if (model == 0 && layer == 2) {
+    p.out = out; p.ldo = c->dims.embed_dim; p.n_valid = c->dims.embed_dim; p.out_f32 = 1;
+    return launch_gemm<EPI_TANH>(c, l, ta, p, s);
+  }
+  if (model == 1 && layer == 1) {
+    p.w3 = c->d_w3_pad; p.b3 = c->d_b3; p.logits = (float*)out;
+    return launch_gemm<EPI_ROWDOT>(c, l, ta, p, s);
+  }
+  p.out = out; p.ldo = l.np; p.n_valid = l.np;
+  return launch_gemm<EPI_LEAKY>(c, l, ta, p, s);
+}
+
 int pbg_check_indices(pbg_ctx* c, void* stream) {
   if (!c) return PBG_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;

@@ -20,7 +20,7 @@ SYMBOLS = (
     "pbg_abi_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_load_generator",
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
-    "pbg_score_triplets_host", "pbg_check_indices", "pbg_launch_count",
+    "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_check_indices", "pbg_launch_count",
 )
 
 
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
         "pbg_discriminator_score_triplets": (C.c_int, [vp, vp, i64, vp, i64, vp, vp, vp, i64, i32, vp]),
         "pbg_score_triplets": (C.c_int, [vp, vp, i64, vp, i64, vp, vp, vp, i32, vp, vp, vp, i64, i32, vp]),
         "pbg_score_triplets_host": (C.c_int, [vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, i32]),
+        "pbg_linear_bf16": (C.c_int, [vp, i32, i32, vp, vp, i64, vp]),
         "pbg_check_indices": (C.c_int, [vp, vp]),
         "pbg_launch_count": (i64, [vp]),
     }

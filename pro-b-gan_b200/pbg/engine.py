@@ -156,6 +156,23 @@ class Engine:
                 self._stream()), self._h)
         return logits, probs
 
+    def linear_bf16(self, model: int, layer: int, a_bf16: torch.Tensor) -> torch.Tensor:
+        """Per-layer diagnostic: one tensor-core Linear (+ its fused epilogue) on a bf16 [M, Kp] matrix."""
+        if a_bf16.dtype != torch.bfloat16 or a_bf16.device != self.device or not a_bf16.is_contiguous():
+            raise ValueError("a_bf16 must be a contiguous bf16 tensor on the engine's device")
+        M = a_bf16.shape[0]
+        if model == 0 and layer == 2:
+            out = torch.empty(M, self.E, dtype=torch.float32, device=self.device)
+        elif model == 1 and layer == 1:
+            out = torch.empty(M, dtype=torch.float32, device=self.device)
+        else:
+            width = (self.HG if model == 0 else self.HD)
+            out = torch.empty(M, (width + 127) // 128 * 128, dtype=torch.bfloat16, device=self.device)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_linear_bf16(self._h, model, layer, _ptr(a_bf16), _ptr(out), M, self._stream()),
+                       self._h)
+        return out
+
     # ------------------------------------------------------------------ fused G + D pass
     def score_triplets(self, node_emb, rel_w, triplets, z=None, want_gen_out=False, want_gen_scores=False,
                        want_disc=True, precision=None, out_dtype=torch.float32):

@@ -1,0 +1,313 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Tolerances are the ones BASELINE.json's north_star states:
+  fp32 mode : max-abs <= 1e-4           (config 2, B = 256)
+  bf16 mode : relative error <= 2e-2    (config 3, B = 4096), rel = max|a-b| / max|b| per output tensor
+  gather / index / sampling steps: bit-exact.
+The oracle is builder-defined (the reference ships no model: parity is *unpinned*, see oracle header).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+FP32_ATOL = 1e-4
+BF16_REL = 2e-2
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked tests need a CUDA device (there is no CPU fallback to test)")
+    assert torch.cuda.get_device_capability(0)[0] == 10, "kernels are sm_100a only"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def cuda_models(dev, synth):
+    import modular_prot_b_gan as m
+    G, D = synth.make_models(m.ModularGenerator, m.ModularDiscriminator)
+    return G.to(dev).eval(), D.to(dev).eval()
+
+
+@pytest.fixture(scope="module")
+def engine(cuda_models):
+    import modular_prot_b_gan as m
+    return m.make_fused_engine(*cuda_models)
+
+
+@pytest.fixture(scope="module")
+def dev_tables(tables, dev):
+    node_emb, rel_w = tables
+    return node_emb.to(dev), rel_w.to(dev)
+
+
+def oracle_pass(oracle_models, tables, trip, z):
+    Go, Do = oracle_models
+    node_emb, rel_w = tables
+    with torch.no_grad():
+        h, r, t = node_emb[trip[:, 0]], rel_w[trip[:, 1]], node_emb[trip[:, 2]]
+        g = Go(h, r, z)
+        d = Do(h, r, t)
+    return h, r, t, g, d, F.cosine_similarity(g, t, dim=1), torch.sigmoid(d)
+
+
+# ----------------------------------------------------------------------------- config 2: fp32, B = 256
+def test_fp32_b256_matches_oracle(engine, oracle_models, tables, dev_tables, synth, dev):
+    B = 256
+    trip, z = synth.make_triplets(B), synth.make_latents(B)
+    _, _, _, g, d, cs, pr = oracle_pass(oracle_models, tables, trip, z)
+    res = engine.score_triplets(*dev_tables, trip.to(dev), z.to(dev), want_gen_out=True, want_gen_scores=True,
+                                want_disc=True, precision="fp32")
+    engine.check_indices()
+    assert res["gen_out"].shape == (B, 128) and res["gen_out"].dtype == torch.float32
+    assert res["logits"].shape == (B,)
+    assert (res["gen_out"].cpu() - g).abs().max().item() <= FP32_ATOL
+    assert (res["logits"].cpu() - d).abs().max().item() <= FP32_ATOL
+    assert (res["probs"].cpu() - pr).abs().max().item() <= FP32_ATOL
+    assert (res["gen_scores"].cpu() - cs).abs().max().item() <= FP32_ATOL
+
+
+# ----------------------------------------------------------------------------- config 3: bf16, B = 4096
+def test_bf16_b4096_matches_oracle(engine, oracle_models, tables, dev_tables, synth, dev):
+    B = 4096
+    trip, z = synth.make_triplets(B), synth.make_latents(B)
+    _, _, _, g, d, cs, pr = oracle_pass(oracle_models, tables, trip, z)
+    res = engine.score_triplets(*dev_tables, trip.to(dev), z.to(dev), want_gen_out=True, want_gen_scores=True,
+                                want_disc=True, precision="bf16")
+    engine.check_indices()
+    assert rel_err(res["gen_out"].cpu(), g) <= BF16_REL
+    assert rel_err(res["logits"].cpu(), d) <= BF16_REL
+    assert rel_err(res["probs"].cpu(), pr) <= BF16_REL
+    assert rel_err(res["gen_scores"].cpu(), cs) <= BF16_REL
+    # elementwise with an absolute floor: bf16 has 8 mantissa bits
+    assert torch.allclose(res["gen_out"].cpu(), g, rtol=BF16_REL, atol=2e-2)
+
+
+def test_bf16_output_dtype_bf16(engine, oracle_models, tables, dev_tables, synth, dev):
+    B = 512
+    trip, z = synth.make_triplets(B), synth.make_latents(B)
+    _, _, _, g, *_ = oracle_pass(oracle_models, tables, trip, z)
+    res = engine.score_triplets(*dev_tables, trip.to(dev), z.to(dev), want_gen_out=True, want_disc=False,
+                                precision="bf16", out_dtype=torch.bfloat16)
+    assert res["gen_out"].dtype == torch.bfloat16
+    assert rel_err(res["gen_out"].float().cpu(), g) <= BF16_REL
+
+
+# ----------------------------------------------------------------------------- per-layer known answers
+@pytest.mark.parametrize("M", [1, 128, 200, 1000])
+def test_tensor_core_layers_known_answer(engine, cuda_models, dev, M):
+    """Each tcgen05 Linear against a torch fp32 product of the same bf16-rounded operands."""
+    G, D = cuda_models
+    gl = [(w.to(dev), b.to(dev)) for w, b in G.folded_layers()]
+    dl = [(w.to(dev), b.to(dev)) for w, b in D.folded_layers()]
+    torch.manual_seed(100 + M)
+
+    def lin(a, w, b):
+        return a.float() @ w.bfloat16().float().T + b
+
+    a = (torch.randn(M, 320, device=dev) * 0.5).bfloat16()
+    r0 = F.leaky_relu(lin(a, *gl[0]), 0.2)
+    assert rel_err(eng_out := engine.linear_bf16(0, 0, a).float(), r0) <= 1e-2, "G layer 0"
+    a1 = r0.bfloat16()
+    r1 = F.leaky_relu(lin(a1, *gl[1]), 0.2)
+    assert rel_err(engine.linear_bf16(0, 1, a1).float(), r1) <= 1e-2, "G layer 1"
+    a2 = r1.bfloat16()
+    r2 = torch.tanh(lin(a2, *gl[2]))
+    assert (engine.linear_bf16(0, 2, a2) - r2).abs().max().item() <= 2e-3, "G layer 2 (tanh.approx)"
+    d0 = (torch.randn(M, 384, device=dev) * 0.5).bfloat16()
+    q0 = F.leaky_relu(lin(d0, *dl[0]), 0.2)
+    assert rel_err(engine.linear_bf16(1, 0, d0).float(), q0) <= 1e-2, "D layer 0"
+    d1 = q0.bfloat16()
+    q1 = F.leaky_relu(lin(d1, *dl[1]), 0.2) @ dl[2][0].reshape(-1) + dl[2][1]
+    assert (engine.linear_bf16(1, 1, d1) - q1).abs().max().item() <= 1e-3, "D layer 1 + folded final dot"
+    del eng_out
+
+
+# ----------------------------------------------------------------------------- bit-exact steps
+def test_gather_is_bit_exact(engine, dev_tables, synth, dev):
+    """forward-with-gather == forward on torch-gathered rows, bit for bit (fp32 mode: the only difference between the
+    two calls is who performs the gather)."""
+    B = 777
+    trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
+    node_emb, rel_w = dev_tables
+    a = engine.generator_forward_gather(node_emb, rel_w, trip[:, 0], trip[:, 1], z, precision="fp32")
+    b = engine.generator_forward(node_emb[trip[:, 0]], rel_w[trip[:, 1]], z, precision="fp32")
+    assert torch.equal(a, b)
+    a = engine.generator_forward_gather(node_emb, rel_w, trip[:, 0], trip[:, 1], z, precision="bf16")
+    b = engine.generator_forward(node_emb[trip[:, 0]], rel_w[trip[:, 1]], z, precision="bf16")
+    assert torch.equal(a, b)
+    la = engine.score_triplets(node_emb, rel_w, trip, precision="fp32")["logits"]
+    lb, _ = engine.discriminator_forward(node_emb[trip[:, 0]], rel_w[trip[:, 1]], node_emb[trip[:, 2]], precision="fp32")
+    assert torch.equal(la, lb)
+
+
+def test_latent_sampling_is_bit_exact(cuda_models, oracle_models):
+    G, _ = cuda_models
+    Go, _ = oracle_models
+    G.reseed(99); Go.reseed(99)
+    assert torch.equal(G.sample_latent(33), Go.sample_latent(33))
+    G.reseed(); Go.reseed()
+
+
+# ----------------------------------------------------------------------------- module boundary
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("B", [1, 16, 127, 129, 255])
+def test_module_boundary_ragged_batches(cuda_models, oracle_models, tables, synth, dev, B, prec):
+    G, D = cuda_models
+    G.precision = D.precision = prec
+    try:
+        trip, z = synth.make_triplets(B, seed=B), synth.make_latents(B, seed=B)
+        h, r, t, g, d, _, pr = oracle_pass(oracle_models, tables, trip, z)
+        node_emb, rel_w = tables
+        out = G(h.to(dev), r.to(dev), z.to(dev))
+        assert out.shape == (B, 128) and out.dtype == torch.float32 and out.is_contiguous()
+        logits = D(h.to(dev), r.to(dev), t.to(dev))
+        assert logits.dim() == 1 and logits.shape == (B,)  # 1-D: the REPL formats [0] with :.4f (:399-400)
+        if B == 1:
+            assert isinstance(logits.item(), float)  # pro_b_gan_infer.py:301
+        rel_emb = torch.nn.Embedding(rel_w.shape[0], rel_w.shape[1]).to(dev)
+        rel_emb.load_state_dict({"weight": rel_w})
+        lg, pb = D.score_triplets(torch.nn.Parameter(node_emb.to(dev), requires_grad=False), rel_emb, trip.to(dev))
+        if prec == "fp32":
+            assert (out.cpu() - g).abs().max().item() <= FP32_ATOL
+            assert (logits.cpu() - d).abs().max().item() <= FP32_ATOL
+            assert (lg.cpu() - d).abs().max().item() <= FP32_ATOL
+            assert (pb.cpu() - pr).abs().max().item() <= FP32_ATOL
+        else:
+            assert (out.cpu() - g).abs().max().item() <= BF16_REL * g.abs().max().item()
+            assert (logits.cpu() - d).abs().max().item() <= BF16_REL * max(d.abs().max().item(), 0.05)
+            assert (lg.cpu() - d).abs().max().item() <= BF16_REL * max(d.abs().max().item(), 0.05)
+        assert len(lg.tolist()) == B and len(pb.tolist()) == B  # :208-209
+    finally:
+        G.precision = D.precision = None
+
+
+def test_generator_draws_its_own_latents_like_the_oracle(cuda_models, oracle_models, tables, synth, dev):
+    """forward(h, r) with no z: both modules draw from a CPU generator seeded 1234 (bit-exact sampling)."""
+    G, _ = cuda_models
+    Go, _ = oracle_models
+    G.reseed(); Go.reseed()
+    node_emb, rel_w = tables
+    trip = synth.make_triplets(64)
+    h, r = node_emb[trip[:, 0]], rel_w[trip[:, 1]]
+    G.precision = "fp32"
+    try:
+        with torch.no_grad():
+            ref = Go(h, r)
+        out = G(h.to(dev), r.to(dev))
+        assert (out.cpu() - ref).abs().max().item() <= FP32_ATOL
+    finally:
+        G.precision = None
+        G.reseed(); Go.reseed()
+
+
+def test_noncontiguous_index_columns(engine, dev_tables, synth, dev):
+    """`triplet_tensor[:, i]` are stride-3 views (pro_b_gan_infer.py:183)."""
+    trip = synth.make_triplets(300).to(dev)
+    z = synth.make_latents(300).to(dev)
+    node_emb, rel_w = dev_tables
+    a = engine.generator_forward_gather(node_emb, rel_w, trip[:, 0], trip[:, 1], z, precision="fp32")
+    b = engine.generator_forward_gather(node_emb, rel_w, trip[:, 0].contiguous(), trip[:, 1].contiguous(), z,
+                                        precision="fp32")
+    assert not trip[:, 0].is_contiguous()
+    assert torch.equal(a, b)
+
+
+def test_out_of_range_index_raises_indexerror(cuda_models, engine, dev_tables, synth, dev):
+    """The CPU reference raises IndexError from `node_emb[heads]`; the CUDA path must too, without a sticky fault."""
+    _, D = cuda_models
+    node_emb, rel_w = dev_tables
+    trip = synth.make_triplets(40).clone()
+    trip[7, 2] = node_emb.shape[0] + 5
+    rel_emb = torch.nn.Embedding(rel_w.shape[0], rel_w.shape[1]).to(dev)
+    with pytest.raises(IndexError):
+        D.score_triplets(node_emb, rel_emb, trip.to(dev))
+    trip[7, 2] = 3
+    trip[0, 1] = -1
+    with pytest.raises(IndexError):
+        D.score_triplets(node_emb, rel_emb, trip.to(dev))
+    # the device is still healthy and the flag is cleared
+    trip[0, 1] = 0
+    D.score_triplets(node_emb, rel_emb, trip.to(dev))
+    torch.cuda.synchronize()
+
+
+def test_empty_batch(engine, dev_tables, dev):
+    node_emb, rel_w = dev_tables
+    res = engine.score_triplets(node_emb, rel_w, torch.empty(0, 3, dtype=torch.int64, device=dev),
+                                torch.empty(0, 64, device=dev), want_gen_out=True, want_disc=True)
+    assert res["gen_out"].shape == (0, 128) and res["logits"].shape == (0,)
+
+
+def test_unloaded_model_and_cpu_module_fail_loudly(dev):
+    import modular_prot_b_gan as m
+    from pbg.engine import Engine
+    from pbg.cabi import PbgError
+    eng = Engine(128, 64, 1024, 1024, dev)
+    with pytest.raises(PbgError):
+        eng.discriminator_forward(torch.zeros(4, 128, device=dev), torch.zeros(4, 128, device=dev),
+                                  torch.zeros(4, 128, device=dev))
+    G = m.ModularGenerator(128, 64).eval()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        G(torch.zeros(2, 128), torch.zeros(2, 128))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m.ModularGenerator(128, 64).to(dev)(torch.zeros(2, 128, device=dev), torch.zeros(2, 128, device=dev))
+
+
+# ----------------------------------------------------------------------------- host-buffer (end-to-end) entry point
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_host_entry_point_matches_device_entry_point(engine, dev_tables, synth, dev, prec):
+    B = 1500
+    trip, z = synth.make_triplets(B).pin_memory(), synth.make_latents(B).pin_memory()
+    node_emb, rel_w = dev_tables
+    gen = torch.empty(B, 128).pin_memory(); sc = torch.empty(B).pin_memory()
+    lg = torch.empty(B).pin_memory(); pb = torch.empty(B).pin_memory()
+    engine.score_triplets_host(node_emb, rel_w, trip, z, gen, sc, lg, pb, precision=prec)
+    res = engine.score_triplets(node_emb, rel_w, trip.to(dev), z.to(dev), want_gen_out=True, want_gen_scores=True,
+                                want_disc=True, precision=prec)
+    assert torch.equal(gen, res["gen_out"].cpu()) and torch.equal(sc, res["gen_scores"].cpu())
+    assert torch.equal(lg, res["logits"].cpu()) and torch.equal(pb, res["probs"].cpu())
+    bad = trip.clone(); bad[3, 0] = 10 ** 9
+    with pytest.raises(IndexError):
+        engine.score_triplets_host(node_emb, rel_w, bad, z, gen, sc, lg, pb, precision=prec)
+
+
+# ----------------------------------------------------------------------------- full-size, size-independent properties
+def test_full_size_properties_b32768(engine, dev_tables, synth, dev):
+    """BASELINE config 4 batch (32768) on one GPU: the oracle is too slow to be the checker at this size in a unit
+    test, so check properties that hold for any correct batched row-wise map:
+      * permutation equivariance: permuting the triplets permutes the outputs, bit for bit;
+      * chunk invariance: the first 4096 rows of the big batch equal a 4096-row call, bit for bit;
+      * duplicated rows give identical outputs; sigmoid(logit) == prob."""
+    B = 32768
+    trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
+    trip[1] = trip[0]; z[1] = z[0]
+    node_emb, rel_w = dev_tables
+    kw = dict(want_gen_out=True, want_gen_scores=True, want_disc=True, precision="bf16")
+    full = engine.score_triplets(node_emb, rel_w, trip, z, **kw)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(5)).to(dev)
+    shuf = engine.score_triplets(node_emb, rel_w, trip[perm], z[perm], **kw)
+    for k in ("gen_out", "gen_scores", "logits", "probs"):
+        assert torch.equal(full[k][perm], shuf[k]), k
+    head = engine.score_triplets(node_emb, rel_w, trip[:4096], z[:4096], **kw)
+    for k in ("gen_out", "gen_scores", "logits", "probs"):
+        assert torch.equal(full[k][:4096], head[k]), k
+    assert torch.equal(full["gen_out"][0], full["gen_out"][1]) and full["logits"][0] == full["logits"][1]
+    assert torch.allclose(torch.sigmoid(full["logits"]), full["probs"], atol=1e-6)
+    assert torch.isfinite(full["gen_out"]).all() and full["gen_out"].abs().max() <= 1.0
+
+
+def test_batch_larger_than_one_chunk(engine, dev_tables, synth, dev):
+    """Batches above the 65536-row workspace chunk are processed in pieces; results must not depend on it."""
+    B = 65536 + 1000
+    trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
+    node_emb, rel_w = dev_tables
+    full = engine.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_disc=True, precision="bf16")
+    tail = engine.score_triplets(node_emb, rel_w, trip[65536:], z[65536:], want_gen_out=True, want_disc=True,
+                                 precision="bf16")
+    assert torch.equal(full["gen_out"][65536:], tail["gen_out"]) and torch.equal(full["logits"][65536:], tail["logits"])
