@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the PRO-B-GAN inference hot path (generator forward + discriminator scoring).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A *step* is one canonical generator + discriminator pass (ProtBGANInference.score_triplets,
+pro_b_gan_infer.py:186-209, at the tensor boundary) over one batch of synthetic triplets:
+gather h/r/t rows -> G(h, r, z) -> cosine(pred, t) -> D(h, r, t) -> sigmoid.  One sample = one triplet.
+
+Workload (BASELINE.json configs[2] at N = 1, configs[3] at N = 8): bf16 tensor-core mode, 4096 triplets per GPU
+per step, batch-index sharded (weak scaling: 4096 x N triplets per step), outputs re-assembled on every rank
+with an all-gather over NVLink at N > 1.  E = 128, Z = 64, H = 1024, 65536 entities, 64 relations, random-init
+weights with the frozen seeds of pbg/synth.py.
+
+Printed JSON (one line, rank 0):
+  value      samples/s, whole job, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e        same metric through the C-ABI host entry point pbg_score_triplets_host: per step H2D of the
+             triplets + latents from pinned host memory and D2H of predictions / scores / logits / probs
+  roofline   dominant kernel vs the measured bf16 tensor peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (oracle/prot_b_gan_oracle.py, a port: the reference ships no model) on the
+             box's host cores, bounded sample
+`--impl reference` times that CPU oracle alone as the reference arm (the reference is CPU PyTorch code).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT / "pro-b-gan_b200"), str(ROOT)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+E, Z, H = 128, 64, 1024
+NUM_ENTITIES, NUM_RELATIONS = 65536, 64
+FLOP_G = 2 * ((2 * E + Z) * H + H * H + H * E)           # 3 014 656 per sample  
+FLOP_D = 2 * (3 * E * H + H * (H // 2) + (H // 2) * 1)   # 1 836 032 per sample
+FLOP_SAMPLE = FLOP_G + FLOP_D                            # 4 850 688
+L2_BYTES = 126 * 2 ** 20
+METRIC = "generator+discriminator samples/sec (score_triplets pass, bf16 tensor-core mode)"
+
+
+def measured_peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return {"bf16_burst": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "hbm_gbs": d["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+def workload_name(batch: int, world: int) -> str:
+    return (f"score_triplets G+D pass, bf16, {batch} triplets/GPU/step x {world} GPU = {batch * world} per step "
+            f"(BASELINE configs[2] per GPU; configs[3] at 8 GPUs), E={E} Z={Z} H={H}, "
+            f"{NUM_ENTITIES} entities, {NUM_RELATIONS} relations")
+
+
+# ------------------------------------------------------------------------------------------ CPU oracle leg
+def cpu_oracle_pass_factory(batch: int):
+    """Returns (fn, cores): fn() runs one oracle G+D pass over `batch` triplets on the CPU (fp32, all threads)."""
+    import torch.nn.functional as F
+    from oracle import prot_b_gan_oracle as oracle  # checker / baseline only, never the product path
+    from pbg import synth
+    G, D = synth.make_models(oracle.ModularGenerator, oracle.ModularDiscriminator)
+    node_emb, rel_w = synth.make_tables(NUM_ENTITIES, NUM_RELATIONS, E)
+    rel_emb = torch.nn.Embedding(NUM_RELATIONS, E)
+    rel_emb.load_state_dict({"weight": rel_w})
+    trip, z = synth.make_triplets(batch), synth.make_latents(batch)
+
+    def fn():
+        with torch.no_grad():
+            h, r, t = node_emb[trip[:, 0]], rel_emb(trip[:, 1]), node_emb[trip[:, 2]]   # :186-188
+            pred = G(h, r, z)                                                            # :201
+            cs = F.cosine_similarity(pred, t, dim=1)                                     # :202
+            logits, probs = D.score_triplets(node_emb, rel_emb, trip)                    # :207
+        return pred, cs, logits, probs
+
+    return fn, torch.get_num_threads()
+
+
+def time_cpu_oracle(batch: int, budget_s: float, max_reps: int = 200):
+    fn, cores = cpu_oracle_pass_factory(batch)
+    fn()  # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < max_reps and (time.perf_counter() - t0 < budget_s or reps < 3):
+        fn()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return batch * reps / dt, cores, reps, dt
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """Reference arm: the reference's own implementation of the path is CPU PyTorch; its model module is not
+    shipped, so the oracle port is what runs (kind = "port").  Rank 0 only."""
+    if rank != 0:
+        return
+    fn, cores = cpu_oracle_pass_factory(args.batch)
+    t0 = time.perf_counter(); fn(); t_one = time.perf_counter() - t0
+    # bound the whole run to ~2 minutes: shrink the per-step sample if K full batches would take longer
+    sample = args.batch
+    total = (args.steps + args.warmup) * t_one
+    if total > 120.0:
+        sample = max(256, int(args.batch * 120.0 / total) // 256 * 256)
+        fn, cores = cpu_oracle_pass_factory(sample)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch, world), "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} triplets per step x {args.steps} steps, torch {torch.__version__} fp32, "
+                                   f"{cores} threads of {os.cpu_count()} logical cores"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank: int, local_rank: int, world: int) -> None:
+    import torch.distributed as dist
+    import modular_prot_b_gan as m
+    from pbg import synth, shard
+    from pbg.clocks import ClockSampler
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    Bg = B * world
+    K, W = args.steps, args.warmup
+    G, D = synth.make_models(m.ModularGenerator, m.ModularDiscriminator)
+    eng = m.make_fused_engine(G.to(dev), D.to(dev))
+    node_emb, rel_w = (t.to(dev) for t in synth.make_tables(NUM_ENTITIES, NUM_RELATIONS, E))
+
+    # ---- input pool: distinct pre-staged batches whose footprint exceeds L2, visited round-robin
+    per_batch = B * (3 * 8 + Z * 4 + E * 2 + 3 * 4)
+    P = max(8, math.ceil(1.6 * L2_BYTES / per_batch))
+    lo, hi = shard.shard_bounds(Bg, world, rank)
+    pool = []
+    for i in range(P):
+        trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=4321 + i)[lo:hi].contiguous().to(dev)
+        z = synth.make_latents(Bg, Z, seed=1234 + i)[lo:hi].contiguous().to(dev)
+        out = {"gen_out": torch.empty(B, E, dtype=torch.bfloat16, device=dev),
+               "gen_scores": torch.empty(B, dtype=torch.float32, device=dev),
+               "logits": torch.empty(B, dtype=torch.float32, device=dev),
+               "probs": torch.empty(B, dtype=torch.float32, device=dev)}
+        pool.append((trip, z, out))
+    if world > 1:
+        full_gen = torch.empty(Bg, E, dtype=torch.bfloat16, device=dev)
+        full_small = torch.empty(world, 3, B, dtype=torch.float32, device=dev)
+        small = torch.empty(3, B, dtype=torch.float32, device=dev)
+
+    def compute(i: int):
+        trip, z, out = pool[i % P]
+        eng.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
+                           precision="bf16", out_dtype=torch.bfloat16, out=out)
+        return out
+
+    def step(i: int):
+        out = compute(i)
+        if world > 1:  # reassemble the outputs on every rank (north_star: NVLink all-gather)
+            dist.all_gather_into_tensor(full_gen, out["gen_out"])
+            small[0].copy_(out["gen_scores"]); small[1].copy_(out["logits"]); small[2].copy_(out["probs"])
+            dist.all_gather_into_tensor(full_small, small)
+
+    # ---- optional CUDA graphs (single GPU): one graph per pool entry, replayed round-robin
+    use_graphs = args.graphs and world == 1
+    graphs = []
+    compute(0); eng.check_indices()
+    l0 = eng.launch_count
+    compute(0)
+    launches_per_step = eng.launch_count - l0
+    if use_graphs:
+        side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(side):
+            for i in range(P):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    compute(i)
+                graphs.append(g)
+        torch.cuda.synchronize()
+
+        def step(i: int):  # noqa: F811
+            graphs[i % P].replay()
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize(); barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        torch.cuda.synchronize(); barrier()
+        ev0.record()
+        for i in range(K):
+            step(W + i)
+        ev1.record()
+        torch.cuda.synchronize(); barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    eng.check_indices()
+    value = Bg * K / (ms * 1e-3)
+    gpu_launches = launches_per_step * K
+
+    # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+    hp = []
+    for i in range(min(P, 16)):
+        trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=9000 + i)[lo:hi].contiguous().pin_memory()
+        z = synth.make_latents(Bg, Z, seed=9500 + i)[lo:hi].contiguous().pin_memory()
+        hp.append((trip, z))
+    h_gen = torch.empty(B, E).pin_memory(); h_sc = torch.empty(B).pin_memory()
+    h_lg = torch.empty(B).pin_memory(); h_pb = torch.empty(B).pin_memory()
+    Ke = min(K, 2000)
+
+    def e2e_step(i: int):
+        trip, z = hp[i % len(hp)]
+        eng.score_triplets_host(node_emb, rel_w, trip, z, h_gen, h_sc, h_lg, h_pb, precision="bf16")
+
+    for i in range(max(3, min(W, 10))):
+        e2e_step(i)
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        e2e_step(i)  # synchronous: returns after the D2H of this step's results
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e = {"value": Bg * Ke / e2e_s, "unit": "samples/s",
+           "h2d_bytes_per_step": B * (3 * 8 + Z * 4) * world, "d2h_bytes_per_step": B * (E * 4 + 3 * 4) * world,
+           "steps": Ke, "api": "pbg_score_triplets_host (C ABI, pinned host buffers, one sync per step)"}
+
+    # ---- roofline of the dominant kernel: per-kernel CUDA events on the launch stream, same workload
+    peaks = measured_peaks()
+    prof_steps = min(K, 200)
+    eng.profile_enable(True)
+    eng.profile_read()
+    for i in range(prof_steps):
+        compute(i)
+    prof = eng.profile_read()
+    eng.profile_enable(False)
+    flops = {"g_l0": 2 * B * (2 * E + Z) * H, "g_l1": 2 * B * H * H, "g_l2": 2 * B * H * E,
+             "d_l0": 2 * B * 3 * E * H, "d_l1": 2 * B * H * (H // 2) + 2 * B * (H // 2)}
+    kinds = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
+    dom = max((k for k in kinds if k in flops), key=lambda k: prof[k][0])
+    ach = flops[dom] / (kinds[dom]["ms_per_launch"] * 1e-3) / 1e12
+    step_tflops = FLOP_SAMPLE * value / world / 1e12
+    peak = peaks["bf16_burst"]  # timed regions here last well under a second: burst figure
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(dom)
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + ", burst figure",
+                "flops_per_launch": flops[dom], "us_per_launch": kinds[dom]["ms_per_launch"] * 1e3,
+                "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak,
+                               "frac_of_sustained": step_tflops / peaks["bf16_sustained"],
+                               "flops_per_sample": FLOP_SAMPLE},
+                "per_kernel_us": {k: round(v["ms_per_launch"] * 1e3, 3) for k, v in kinds.items()}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, reps, dt = time_cpu_oracle(B, budget_s=12.0)
+            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": f"{reps} passes of {B} triplets in {dt:.1f} s, oracle fp32, torch {torch.__version__}, "
+                             f"{cores} threads of {os.cpu_count()} logical cores"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(B, world), "global_batch": Bg, "parallelism": f"dp{world}",
+                       "l2": f"inputs rotate over {P} distinct pre-staged batches ({P * per_batch / 2**20:.0f} MiB "
+                             f"> 126 MiB L2); no flush", "cuda_graphs": bool(use_graphs),
+                       "collective": "all-gather of outputs (NCCL)" if world > 1 else "none"},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=4096, help="triplets per GPU per step")
+    ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

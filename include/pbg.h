@@ -145,6 +145,23 @@ int pbg_check_indices(pbg_ctx* ctx, void* stream);
 int pbg_linear_bf16(pbg_ctx* ctx, int model, int layer, const void* a_bf16, void* out, int64_t M,
                     void* stream);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, every kernel this ctx launches is
+ * bracketed by CUDA events on its launch stream.  pbg_profile_read synchronises, adds the elapsed
+ * milliseconds and launch counts per kernel kind into ms[PBG_NUM_KERNEL_KINDS] /
+ * count[PBG_NUM_KERNEL_KINDS], and resets the records. */
+enum {
+  PBG_K_GATHER = 0, /* gather + concat (+ bf16 cast)                      */
+  PBG_K_G_L0 = 1,   /* generator Linear 0 (2E+Z -> H) + BN + LeakyReLU    */
+  PBG_K_G_L1 = 2,   /* generator Linear 1 (H -> H) + BN + LeakyReLU       */
+  PBG_K_G_L2 = 3,   /* generator Linear 2 (H -> E) + tanh (+ cosine)      */
+  PBG_K_D_L0 = 4,   /* discriminator Linear 0 (3E -> H) + LeakyReLU       */
+  PBG_K_D_L1 = 5,   /* discriminator Linear 1 (H -> H/2) + LeakyReLU + final dot + sigmoid */
+  PBG_K_OTHER = 6,  /* fp32-mode row-dot / cosine, weight packing         */
+  PBG_NUM_KERNEL_KINDS = 7
+};
+int pbg_profile_enable(pbg_ctx* ctx, int enable);
+int pbg_profile_read(pbg_ctx* ctx, double* ms, int64_t* count);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/pbg.h"
 #include "gather.cuh"
@@ -75,6 +76,9 @@ struct pbg_ctx {
   float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
   EncodeTiledFn encode = nullptr;
   long long launches = 0;
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; int kind; };
+  std::vector<ProfRec> prof;
   std::string err;
 };
 
@@ -89,6 +93,21 @@ int fail(pbg_ctx* c, int code, const char* fmt, ...) {
   if (c) c->err = buf; else g_create_error = buf;
   return code;
 }
+
+// Brackets one kernel launch with events when profiling is on (bench.py roofline), and counts it.
+struct LaunchScope {
+  pbg_ctx* c; cudaStream_t s; cudaEvent_t b = nullptr;
+  LaunchScope(pbg_ctx* c_, int kind, cudaStream_t s_) : c(c_), s(s_) {
+    c->launches += 1;
+    if (c->profiling) {
+      cudaEvent_t a;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+      c->prof.push_back({a, b, kind});
+    }
+  }
+  ~LaunchScope() { if (b) cudaEventRecord(b, s); }
+};
 
 #define PBG_CUDA(c, expr)                                                                               \
   do {                                                                                                  \
@@ -137,9 +156,10 @@ int upload_linear(pbg_ctx* c, Linear& l, int n, int k, int kp, const float* w_ho
   PBG_CUDA(c, cudaMalloc(&l.b_pad, sizeof(float) * l.np));
   PBG_CUDA(c, cudaMemcpyAsync(l.w_f32, w_host, sizeof(float) * n * k, cudaMemcpyHostToDevice, c->own_stream));
   PBG_CUDA(c, cudaMemcpyAsync(l.b_f32, b_host, sizeof(float) * n, cudaMemcpyHostToDevice, c->own_stream));
-  pack_bf16_kernel<<<c->num_sms * 4, 256, 0, c->own_stream>>>(l.w_f32, l.w_bf16, n, k, l.np, l.kp);
-  pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(l.b_f32, l.b_pad, n, l.np);
-  c->launches += 2;
+  { LaunchScope ls(c, PBG_K_OTHER, c->own_stream);
+    pack_bf16_kernel<<<c->num_sms * 4, 256, 0, c->own_stream>>>(l.w_f32, l.w_bf16, n, k, l.np, l.kp); }
+  { LaunchScope ls(c, PBG_K_OTHER, c->own_stream);
+    pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(l.b_f32, l.b_pad, n, l.np); }
   PBG_CUDA(c, cudaGetLastError());
   PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
   return make_tmap(c, &l.tmap_w, l.w_bf16, l.np, l.kp, l.block_n);
@@ -178,7 +198,8 @@ int ensure_ws(pbg_ctx* c, int prec, long long rows) {
 }
 
 template <int BLOCK_N, int STAGES, int EPI>
-int launch_gemm_inst(pbg_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t s) {
+int launch_gemm_inst(pbg_ctx* c, int kind, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                     cudaStream_t s) {
   using L = GemmSmem<BLOCK_N, STAGES>;
   auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, EPI>;
   static bool attr_set = false;  // per instantiation; ctxs on different devices share the function handle
@@ -190,26 +211,26 @@ int launch_gemm_inst(pbg_ctx* c, const CUtensorMap& ta, const CUtensorMap& tb, c
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int items = (EPI == EPI_LEAKY) ? m_tiles * (p.N / BLOCK_N) : m_tiles;
   const int grid = std::max(1, std::min(items, c->num_sms));
-  kern<<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, p);
-  c->launches += 1;
+  { LaunchScope ls(c, kind, s);
+    kern<<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, p); }
   PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
 
 template <int EPI>
-int launch_gemm(pbg_ctx* c, const Linear& l, const CUtensorMap& ta, GemmParams p, cudaStream_t s) {
+int launch_gemm(pbg_ctx* c, int kind, const Linear& l, const CUtensorMap& ta, GemmParams p, cudaStream_t s) {
   p.N = l.np; p.K = l.kp; p.bias = l.b_pad; p.slope = c->dims.leaky_slope;
-  if (l.block_n == 256) return launch_gemm_inst<256, 4, EPI>(c, ta, l.tmap_w, p, s);
-  return launch_gemm_inst<128, 6, EPI>(c, ta, l.tmap_w, p, s);
+  if (l.block_n == 256) return launch_gemm_inst<256, 4, EPI>(c, kind, ta, l.tmap_w, p, s);
+  return launch_gemm_inst<128, 6, EPI>(c, kind, ta, l.tmap_w, p, s);
 }
 
 template <int ACT>
-int launch_f32(pbg_ctx* c, const Linear& l, const float* A, long long lda, float* out, long long ldo, long long M,
+int launch_f32(pbg_ctx* c, int kind, const Linear& l, const float* A, long long lda, float* out, long long ldo, long long M,
                cudaStream_t s) {
   F32GemmParams p{A, lda, l.w_f32, l.k, l.b_f32, out, ldo, (int)M, l.n, l.k, c->dims.leaky_slope};
   dim3 grid((l.n + 63) / 64, (unsigned)((M + 63) / 64));
-  gemm_f32_kernel<ACT><<<grid, 256, 0, s>>>(p);
-  c->launches += 1;
+  { LaunchScope ls(c, kind, s);
+    gemm_f32_kernel<ACT><<<grid, 256, 0, s>>>(p); }
   PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
@@ -243,9 +264,9 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   gp.xd = a.run_d ? w.xd0 : nullptr; gp.ldd = bf ? c->kd0p : c->kd0;
   gp.B = rows; gp.err_flag = c->err_flag;
   const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
-  if (bf) gather_concat_kernel<__nv_bfloat16><<<gather_blocks, 256, 0, s>>>(gp);
-  else    gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp);
-  c->launches += 1;
+  { LaunchScope ls(c, PBG_K_GATHER, s);
+    if (bf) gather_concat_kernel<__nv_bfloat16><<<gather_blocks, 256, 0, s>>>(gp);
+    else    gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp); }
   PBG_CUDA(c, cudaGetLastError());
 
   const size_t out_es = a.out_dtype == PBG_DT_BF16 ? 2 : 4;
@@ -257,49 +278,49 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
       GemmParams p{};
       p.M = (int)rows;
       p.out = w.bufA; p.ldo = c->hgp; p.n_valid = c->hgp;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->g[0], w.tm_xg0, p, s));
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_G_L0, c->g[0], w.tm_xg0, p, s));
       p.out = w.bufB;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->g[1], w.tm_bufA_g, p, s));
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_G_L1, c->g[1], w.tm_bufA_g, p, s));
       GemmParams q{};
       q.M = (int)rows; q.out = gen_out; q.ldo = E; q.n_valid = E; q.out_f32 = a.out_dtype == PBG_DT_F32;
       if (scores) {
         q.cosine = scores; q.tail_tab = a.node_emb; q.n_ent = a.N;
         q.tail_idx = a.tails + off * a.ts; q.tail_stride = a.ts;
       }
-      PBG_TRY(launch_gemm<EPI_TANH>(c, c->g[2], w.tm_bufB_g, q, s));
+      PBG_TRY(launch_gemm<EPI_TANH>(c, PBG_K_G_L2, c->g[2], w.tm_bufB_g, q, s));
     }
     if (a.run_d) {
       GemmParams p{};
       p.M = (int)rows; p.out = w.bufA; p.ldo = c->hdp; p.n_valid = c->hdp;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, c->d[0], w.tm_xd0, p, s));
+      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_D_L0, c->d[0], w.tm_xd0, p, s));
       GemmParams q{};
       q.M = (int)rows; q.w3 = c->d_w3_pad; q.b3 = c->d_b3; q.logits = a.logits + off;
       q.probs = a.probs ? a.probs + off : nullptr;
-      PBG_TRY(launch_gemm<EPI_ROWDOT>(c, c->d[1], w.tm_bufA_d, q, s));
+      PBG_TRY(launch_gemm<EPI_ROWDOT>(c, PBG_K_D_L1, c->d[1], w.tm_bufA_d, q, s));
     }
   } else {
     float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
     const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
     if (a.run_g) {
       const int H = c->dims.g_hidden;
-      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->g[0], xg0, c->kg0, bufA, H, rows, s));
-      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->g[1], bufA, H, bufB, H, rows, s));
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, PBG_K_G_L0, c->g[0], xg0, c->kg0, bufA, H, rows, s));
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, PBG_K_G_L1, c->g[1], bufA, H, bufB, H, rows, s));
       float* pred = gen_out ? (float*)gen_out : bufA;  // bufA is free once layer 2 has consumed it
-      PBG_TRY(launch_f32<ACT_TANH>(c, c->g[2], bufB, H, pred, E, rows, s));
+      PBG_TRY(launch_f32<ACT_TANH>(c, PBG_K_G_L2, c->g[2], bufB, H, pred, E, rows, s));
       if (scores) {
-        cosine_f32_kernel<<<row_blocks, 256, 0, s>>>(pred, E, a.node_emb, a.N, a.tails + off * a.ts, a.ts, E, rows,
-                                                     scores);
-        c->launches += 1;
+        { LaunchScope ls(c, PBG_K_OTHER, s);
+          cosine_f32_kernel<<<row_blocks, 256, 0, s>>>(pred, E, a.node_emb, a.N, a.tails + off * a.ts, a.ts, E, rows,
+                                                       scores); }
         PBG_CUDA(c, cudaGetLastError());
       }
     }
     if (a.run_d) {
       const int H = c->dims.d_hidden, H2 = c->hd2;
-      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->d[0], xd0, c->kd0, bufA, H, rows, s));
-      PBG_TRY(launch_f32<ACT_LEAKY>(c, c->d[1], bufA, H, bufB, H2, rows, s));
-      rowdot_f32_kernel<<<row_blocks, 256, 0, s>>>(bufB, H2, c->d_w3, c->d_b3, H2, rows, a.logits + off,
-                                                   a.probs ? a.probs + off : nullptr);
-      c->launches += 1;
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, PBG_K_D_L0, c->d[0], xd0, c->kd0, bufA, H, rows, s));
+      PBG_TRY(launch_f32<ACT_LEAKY>(c, PBG_K_D_L1, c->d[1], bufA, H, bufB, H2, rows, s));
+      { LaunchScope ls(c, PBG_K_OTHER, s);
+        rowdot_f32_kernel<<<row_blocks, 256, 0, s>>>(bufB, H2, c->d_w3, c->d_b3, H2, rows, a.logits + off,
+                                                     a.probs ? a.probs + off : nullptr); }
       PBG_CUDA(c, cudaGetLastError());
     }
   }
@@ -434,8 +455,8 @@ int pbg_load_discriminator(pbg_ctx* c, const float* p, size_t n_floats) {
   PBG_CUDA(c, cudaMalloc(&c->d_w3, sizeof(float) * H2));
   PBG_CUDA(c, cudaMalloc(&c->d_w3_pad, sizeof(float) * np));
   PBG_CUDA(c, cudaMemcpyAsync(c->d_w3, w3, sizeof(float) * H2, cudaMemcpyHostToDevice, c->own_stream));
-  pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(c->d_w3, c->d_w3_pad, (int)H2, np);
-  c->launches += 1;
+  { LaunchScope ls(c, PBG_K_OTHER, c->own_stream);
+    pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(c->d_w3, c->d_w3_pad, (int)H2, np); }
   PBG_CUDA(c, cudaGetLastError());
   PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
   c->d_b3 = *b3;
@@ -509,14 +530,35 @@ int pbg_linear_bf16(pbg_ctx* c, int model, int layer, const void* a, void* out, 
   p.M = (int)M;
   if (model == 0 && layer == 2) {
     p.out = out; p.ldo = c->dims.embed_dim; p.n_valid = c->dims.embed_dim; p.out_f32 = 1;
-    return launch_gemm<EPI_TANH>(c, l, ta, p, s);
+    return launch_gemm<EPI_TANH>(c, PBG_K_G_L2, l, ta, p, s);
   }
   if (model == 1 && layer == 1) {
     p.w3 = c->d_w3_pad; p.b3 = c->d_b3; p.logits = (float*)out;
-    return launch_gemm<EPI_ROWDOT>(c, l, ta, p, s);
+    return launch_gemm<EPI_ROWDOT>(c, PBG_K_D_L1, l, ta, p, s);
   }
   p.out = out; p.ldo = l.np; p.n_valid = l.np;
-  return launch_gemm<EPI_LEAKY>(c, l, ta, p, s);
+  return launch_gemm<EPI_LEAKY>(c, model == 0 ? PBG_K_G_L0 + layer : PBG_K_D_L0 + layer, l, ta, p, s);
+}
+
+int pbg_profile_enable(pbg_ctx* c, int enable) {
+  if (!c) return PBG_ERR_INVALID;
+  c->profiling = enable != 0;
+  return PBG_OK;
+}
+
+int pbg_profile_read(pbg_ctx* c, double* ms, int64_t* count) {
+  if (!c || !ms || !count) return PBG_ERR_INVALID;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  PBG_CUDA(c, cudaDeviceSynchronize());
+  for (auto& r : c->prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.kind >= 0 && r.kind < PBG_NUM_KERNEL_KINDS) {
+      ms[r.kind] += t; count[r.kind] += 1;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  c->prof.clear();
+  return PBG_OK;
 }
 
 int pbg_check_indices(pbg_ctx* c, void* stream) {

@@ -111,6 +111,17 @@ class Engine:
         """Synchronise and raise IndexError if a gather since the last check saw an out-of-range id."""
         cabi.check(self._lib.pbg_check_indices(self._h, self._stream()), self._h)
 
+    def profile_enable(self, on: bool = True) -> None:
+        cabi.check(self._lib.pbg_profile_enable(self._h, 1 if on else 0), self._h)
+
+    def profile_read(self) -> dict:
+        """{kind: (total_ms, launches)} since the last read; synchronises the device."""
+        n = len(cabi.KERNEL_KINDS)
+        ms = (C.c_double * n)(*([0.0] * n))
+        cnt = (C.c_int64 * n)(*([0] * n))
+        cabi.check(self._lib.pbg_profile_read(self._h, ms, cnt), self._h)
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(cabi.KERNEL_KINDS)}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.pbg_launch_count(self._h))
@@ -175,8 +186,11 @@ class Engine:
 
     # ------------------------------------------------------------------ fused G + D pass
     def score_triplets(self, node_emb, rel_w, triplets, z=None, want_gen_out=False, want_gen_scores=False,
-                       want_disc=True, precision=None, out_dtype=torch.float32):
-        """One gather feeding G and/or D.  Returns dict with the requested tensors."""
+                       want_disc=True, precision=None, out_dtype=torch.float32, out: dict | None = None):
+        """One gather feeding G and/or D.  Returns dict with the requested tensors.
+
+        ``out`` may carry preallocated result tensors (keys gen_out / gen_scores / logits / probs) so that a
+        steady-state caller (bench.py, CUDA-graph capture) performs no allocation per call."""
         node_emb = self._f32(node_emb, self.E, "node_emb")
         rel_w = self._f32(rel_w, self.E, "rel_emb.weight")
         trip = self._i64(triplets, "triplets")
@@ -190,10 +204,22 @@ class Engine:
                 raise ValueError("generator pass needs latents z")
             z = self._f32(z, self.Z, "z")
         res = {}
-        gen_out = torch.empty(B, self.E, dtype=out_dtype, device=self.device) if want_gen_out else None
-        scores = torch.empty(B, dtype=torch.float32, device=self.device) if want_gen_scores else None
-        logits = torch.empty(B, dtype=torch.float32, device=self.device) if want_disc else None
-        probs = torch.empty(B, dtype=torch.float32, device=self.device) if want_disc else None
+        out = out or {}
+
+        def buf(key, want, shape, dtype):
+            if not want:
+                return None
+            t = out.get(key)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=self.device)
+            if tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+                raise ValueError(f"out[{key!r}] must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}")
+            return t
+
+        gen_out = buf("gen_out", want_gen_out, (B, self.E), out_dtype)
+        scores = buf("gen_scores", want_gen_scores, (B,), torch.float32)
+        logits = buf("logits", want_disc, (B,), torch.float32)
+        probs = buf("probs", want_disc, (B,), torch.float32)
         with torch.cuda.device(self.device):
             cabi.check(self._lib.pbg_score_triplets(
                 self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(trip),
