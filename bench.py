@@ -272,6 +272,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     eng.profile_enable(False)
     flops = {"g_l0": 2 * B * (2 * E + Z) * H, "g_l1": 2 * B * H * H, "g_l2": 2 * B * H * E,
              "d_l0": 2 * B * 3 * E * H, "d_l1": 2 * B * H * (H // 2) + 2 * B * (H // 2)}
+    flops["pass"] = B * FLOP_SAMPLE  # the fused kernel runs the whole G + D pass
     kinds = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
     dom = max((k for k in kinds if k in flops), key=lambda k: prof[k][0])
     ach = flops[dom] / (kinds[dom]["ms_per_launch"] * 1e-3) / 1e12

@@ -157,10 +157,18 @@ enum {
   PBG_K_D_L0 = 4,   /* discriminator Linear 0 (3E -> H) + LeakyReLU       */
   PBG_K_D_L1 = 5,   /* discriminator Linear 1 (H -> H/2) + LeakyReLU + final dot + sigmoid */
   PBG_K_OTHER = 6,  /* fp32-mode row-dot / cosine, weight packing         */
-  PBG_NUM_KERNEL_KINDS = 7
+  PBG_K_PASS = 7,   /* bf16 mode: the whole G + D pass as one persistent kernel (gather + 5 Linear layers) */
+  PBG_NUM_KERNEL_KINDS = 8
 };
 int pbg_profile_enable(pbg_ctx* ctx, int enable);
 int pbg_profile_read(pbg_ctx* ctx, double* ms, int64_t* count);
+
+/* Diagnostics: while enabled, the tensor-core kernels write clock64 slots per CTA (begin, producer / MMA /
+ * epilogue wait sums, end stamps and a per-item timeline; layout in pass_kernel.cuh) into a device buffer of
+ * 256 x num_SMs slots.
+ * The call synchronises the device, copies the current slots to host_out (if non-NULL, up to n_slots),
+ * then enables / disables tracing and zeroes the buffer. */
+int pbg_debug_trace(pbg_ctx* ctx, int enable, int64_t* host_out, int64_t n_slots);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);

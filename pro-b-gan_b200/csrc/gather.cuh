@@ -48,8 +48,12 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, float4
   *reinterpret_cast<uint2*>(dst) = w;
 }
 
+// streaming 128-bit read: rows are touched once, keep them out of L1 (the epilogues' bias lines live there)
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
-  return __ldg(reinterpret_cast<const float4*>(p));
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
 
 template <typename T>

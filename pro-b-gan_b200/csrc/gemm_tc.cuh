@@ -49,6 +49,7 @@ struct GemmParams {
   long long tail_stride;
   long long n_ent;
   float* cosine;             // [M]
+  long long* trace;          // diagnostics: 16 clock64 slots per CTA (pbg_debug_trace), or nullptr
 };
 
 template <int BLOCK_N, int STAGES>
@@ -120,17 +121,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* tr = p.trace ? p.trace + 256 * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         for (int u = 0; u < units_per_item; ++u) {
           const int m_blk = kRowItems ? item : item / n_tiles;
           const int n_blk = kRowItems ? u : item % n_tiles;
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
+            else mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -140,19 +145,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
       }
+      if (tr) { tr[1] = w_empty; tr[2] = clock64(); }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      long long w_full = 0, w_tmem = 0, t_first = 0, n_kb = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         for (int u = 0; u < units_per_item; ++u) {
-          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+          if (tr) { const long long t = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
+          else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
+            if (tr) {
+              const long long t = clock64(); mbar_wait(&full_bar[stage], phase); const long long t2 = clock64();
+              w_full += t2 - t; if (n_kb++ == 0) t_first = t2;
+            } else mbar_wait(&full_bar[stage], phase);  // TMA bytes have landed
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
             const uint64_t da = make_kmajor_sw128_desc(sa);
@@ -169,12 +180,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
+      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[5] = t_first; tr[6] = clock64(); tr[9] = n_kb; }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     uint32_t acc = 0, acc_phase = 0;
+    long long w_acc = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int m_blk = kRowItems ? item : item / n_tiles;
       const long long grow = static_cast<long long>(m_blk) * kBlockM + q * 32 + lane;
@@ -189,7 +202,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       for (int u = 0; u < units_per_item; ++u) {
         const int n_blk = kRowItems ? u : item % n_tiles;
-        mbar_wait(&tmem_full[acc], acc_phase);
+        if (tr && threadIdx.x == 64) { const long long t = clock64(); mbar_wait(&tmem_full[acc], acc_phase); w_acc += clock64() - t; tr[10] = clock64(); }
+        else mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
@@ -285,6 +299,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         p.cosine[grow] = cs_dot / (np * nt);
       }
     }
+    if (tr && threadIdx.x == 64) { tr[7] = w_acc; tr[8] = clock64(); }
   }
 
   tc_fence_before();

@@ -15,6 +15,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <new>
 #include <string>
 #include <vector>
@@ -23,12 +25,15 @@
 #include "gather.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
+#include "pass_kernel.cuh"
 
 using namespace pbg;
 
 namespace {
 
 constexpr long long kMaxChunk = 65536;  // rows processed per launch sequence (bounds the workspaces)
+constexpr int kPartSlotsG = 16;  // generator cosine partials per row: one per 32 output columns (E <= 512)
+constexpr int kPartSlotsD = 64;  // discriminator dot partials per row: one per 64 columns of H/2 (H <= 8192)
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -40,13 +45,29 @@ struct Linear {
   float* b_f32 = nullptr;
   __nv_bfloat16* w_bf16 = nullptr;
   float* b_pad = nullptr;
-  CUtensorMap tmap_w;
+  CUtensorMap tmap_w;     // box 64 x block_n
+  CUtensorMap tmap_w128;  // box 64 x 128 (finer tiles for small batches)
 };
 
 struct Workspace {
   long long rows = 0;
-  void *xg0 = nullptr, *xd0 = nullptr, *bufA = nullptr, *bufB = nullptr;
-  CUtensorMap tm_xg0, tm_xd0, tm_bufA_g, tm_bufA_d, tm_bufB_g;
+  void *xg0 = nullptr, *xd0 = nullptr, *bufA = nullptr, *bufB = nullptr, *bufD = nullptr;
+  CUtensorMap tm_xg0, tm_xd0, tm_bufA_g, tm_bufA_d, tm_bufB_g, tm_bufD_d;
+  CUtensorMap tmo_bufA, tmo_bufB, tmo_bufD;  // store maps: box 64 x 32 (one epilogue warp's chunk)
+  // fused pass kernel state (bf16 mode): arrival counters, scheduler, row-reduction partials
+  int mb_cap = 0;
+  int* ready = nullptr;   // [DEP_KINDS][mb_cap]
+  int* fin = nullptr;     // [FIN_KINDS][mb_cap]
+  PassSched* sched = nullptr;
+  float* part_g = nullptr;  // [mb_cap][4][3][128]
+  float* part_d = nullptr;  // [mb_cap][2 * max n_tiles][128]
+};
+
+struct ItemList {
+  uint2* dev = nullptr;
+  int n = 0;
+  int block_n[5] = {128, 128, 128, 128, 128};
+  int phase0_groups = 0;
 };
 
 thread_local std::string g_create_error;
@@ -75,8 +96,10 @@ struct pbg_ctx {
   long long* st_trip = nullptr;
   float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
   EncodeTiledFn encode = nullptr;
+  std::map<std::tuple<long long, int, int>, ItemList> item_cache;  // (rows, run_g, run_d) -> work-item order
   long long launches = 0;
   bool profiling = false;
+  long long* trace = nullptr;  // device, 16 slots x num_sms (pbg_debug_trace)
   struct ProfRec { cudaEvent_t a, b; int kind; };
   std::vector<ProfRec> prof;
   std::string err;
@@ -140,7 +163,8 @@ void free_linear(Linear& l) {
 }
 
 void free_ws(Workspace& w) {
-  cudaFree(w.xg0); cudaFree(w.xd0); cudaFree(w.bufA); cudaFree(w.bufB);
+  cudaFree(w.xg0); cudaFree(w.xd0); cudaFree(w.bufA); cudaFree(w.bufB); cudaFree(w.bufD);
+  cudaFree(w.ready); cudaFree(w.fin); cudaFree(w.sched); cudaFree(w.part_g); cudaFree(w.part_d);
   w = Workspace{};
 }
 
@@ -162,6 +186,7 @@ int upload_linear(pbg_ctx* c, Linear& l, int n, int k, int kp, const float* w_ho
     pad_f32_kernel<<<8, 256, 0, c->own_stream>>>(l.b_f32, l.b_pad, n, l.np); }
   PBG_CUDA(c, cudaGetLastError());
   PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
+  PBG_TRY(make_tmap(c, &l.tmap_w128, l.w_bf16, l.np, l.kp, 128));
   return make_tmap(c, &l.tmap_w, l.w_bf16, l.np, l.kp, l.block_n);
 }
 
@@ -180,6 +205,20 @@ int ensure_ws(pbg_ctx* c, int prec, long long rows) {
     PBG_CUDA(c, cudaMalloc(&w.xd0, es * cap * c->kd0p));
     PBG_CUDA(c, cudaMalloc(&w.bufA, es * cap * c->hmax));
     PBG_CUDA(c, cudaMalloc(&w.bufB, es * cap * c->hmax));
+    PBG_CUDA(c, cudaMalloc(&w.bufD, es * cap * c->hdp));
+    PBG_TRY(make_tmap(c, &w.tm_bufD_d, w.bufD, cap, c->hdp, kBlockM));
+    PBG_TRY(make_tmap(c, &w.tmo_bufA, w.bufA, cap, c->hgp, 32));
+    PBG_TRY(make_tmap(c, &w.tmo_bufB, w.bufB, cap, c->hgp, 32));
+    PBG_TRY(make_tmap(c, &w.tmo_bufD, w.bufD, cap, c->hdp, 32));
+    w.mb_cap = static_cast<int>(cap / kBlockM);
+    PBG_CUDA(c, cudaMalloc(&w.ready, sizeof(int) * DEP_KINDS * w.mb_cap));
+    PBG_CUDA(c, cudaMalloc(&w.fin, sizeof(int) * FIN_KINDS * w.mb_cap));
+    PBG_CUDA(c, cudaMalloc(&w.sched, sizeof(PassSched)));
+    PBG_CUDA(c, cudaMalloc(&w.part_g, sizeof(float) * w.mb_cap * kPartSlotsG * 3 * kBlockM));
+    PBG_CUDA(c, cudaMalloc(&w.part_d, sizeof(float) * w.mb_cap * kPartSlotsD * kBlockM));
+    PBG_CUDA(c, cudaMemset(w.ready, 0, sizeof(int) * DEP_KINDS * w.mb_cap));
+    PBG_CUDA(c, cudaMemset(w.fin, 0, sizeof(int) * FIN_KINDS * w.mb_cap));
+    PBG_CUDA(c, cudaMemset(w.sched, 0, sizeof(PassSched)));
     PBG_TRY(make_tmap(c, &w.tm_xg0, w.xg0, cap, c->kg0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_xd0, w.xd0, cap, c->kd0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_bufA_g, w.bufA, cap, c->hgp, kBlockM));
@@ -219,7 +258,7 @@ int launch_gemm_inst(pbg_ctx* c, int kind, const CUtensorMap& ta, const CUtensor
 
 template <int EPI>
 int launch_gemm(pbg_ctx* c, int kind, const Linear& l, const CUtensorMap& ta, GemmParams p, cudaStream_t s) {
-  p.N = l.np; p.K = l.kp; p.bias = l.b_pad; p.slope = c->dims.leaky_slope;
+  p.N = l.np; p.K = l.kp; p.bias = l.b_pad; p.slope = c->dims.leaky_slope; p.trace = c->trace;
   if (l.block_n == 256) return launch_gemm_inst<256, 4, EPI>(c, kind, ta, l.tmap_w, p, s);
   return launch_gemm_inst<128, 6, EPI>(c, kind, ta, l.tmap_w, p, s);
 }
@@ -234,6 +273,164 @@ int launch_f32(pbg_ctx* c, int kind, const Linear& l, const float* A, long long 
   PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Work-item order of the fused pass kernel.  CTAs claim items in list order, so the list must be a topological
+// order of the dependency graph (gather -> L0 -> L1 -> L2 per 128-row block); which topological order decides how
+// well the tail balances.  The order is produced by list scheduling on a coarse cost model: simulate num_SMs
+// workers, always hand the next free worker the ready item with the longest remaining critical path (or, if none
+// is ready, the one that becomes ready first).  Items of one layer are considered in row-block order, so the
+// candidate set is the front of six queues.
+struct LayerPlan { int num_kb, bn, n_tiles; };
+
+int clk_per_kb(int bn) { return bn >= 256 ? 512 : (bn >= 128 ? 340 : 260); }
+
+int build_items(pbg_ctx* c, long long rows, bool run_g, bool run_d, ItemList** out) {
+  const auto key = std::make_tuple(rows, static_cast<int>(run_g), static_cast<int>(run_d));
+  auto hit = c->item_cache.find(key);
+  if (hit != c->item_cache.end()) { *out = &hit->second; return PBG_OK; }
+  if (c->item_cache.size() >= 64) {
+    PBG_CUDA(c, cudaDeviceSynchronize());
+    for (auto& kv : c->item_cache) cudaFree(kv.second.dev);
+    c->item_cache.clear();
+  }
+  const int mb = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+  const int P = c->num_sms;
+  const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
+  const bool on[6] = {run_g, run_d, run_g, run_d, run_g, true};
+  LayerPlan plan[5];
+  ItemList il;
+  for (int k = 0; k < 5; ++k) {
+    plan[k] = LayerPlan{0, 128, 0};
+    if (!on[k]) continue;
+    int bn = lin[k]->block_n;
+    if (bn == 256 && static_cast<long long>(mb) * (lin[k]->np / 256) < P / 2) bn = 128;  // small batch: finer tiles
+    plan[k] = LayerPlan{lin[k]->kp / kBlockK, bn, lin[k]->np / bn};
+    il.block_n[k] = bn;
+    if (plan[k].n_tiles > 255) return fail(c, PBG_ERR_UNSUPPORTED, "layer too wide for the tile index");
+  }
+  if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
+  if (on[IT_G_L2] && lin[IT_G_L2]->np / 32 > kPartSlotsG) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
+
+  static const int pred_of[6] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1, -1};
+  static const int out_of[6] = {DEP_G0, DEP_D0, DEP_G1, -1, -1, DEP_X};
+  auto units_of = [&](int m) {
+    const long long r = std::min<long long>(kBlockM, rows - static_cast<long long>(m) * kBlockM);
+    return static_cast<int>((r + kGatherRows - 1) / kGatherRows);
+  };
+  auto per_block = [&](int kind, int m) { return kind == IT_GATHER ? units_of(m) : plan[kind].n_tiles; };
+  long long cost[6], lat[6], rank[6];
+  for (int k = 0; k < 5; ++k) { cost[k] = static_cast<long long>(plan[k].num_kb) * clk_per_kb(plan[k].bn) + 300; lat[k] = 1500; }
+  cost[IT_GATHER] = 1200; lat[IT_GATHER] = 5000;
+  rank[IT_G_L2] = cost[IT_G_L2];
+  rank[IT_G_L1] = cost[IT_G_L1] + lat[IT_G_L1] + rank[IT_G_L2];
+  rank[IT_G_L0] = cost[IT_G_L0] + lat[IT_G_L0] + rank[IT_G_L1];
+  rank[IT_D_L1] = cost[IT_D_L1];
+  rank[IT_D_L0] = cost[IT_D_L0] + lat[IT_D_L0] + rank[IT_D_L1];
+  rank[IT_GATHER] = 1LL << 40;
+
+  std::vector<int> emitted(DEP_KINDS * mb, 0), total(DEP_KINDS * mb, 0);
+  std::vector<long long> finish(DEP_KINDS * mb, 0);
+  for (int m = 0; m < mb; ++m) {
+    total[DEP_X * mb + m] = units_of(m);
+    total[DEP_G0 * mb + m] = plan[IT_G_L0].n_tiles;
+    total[DEP_D0 * mb + m] = plan[IT_D_L0].n_tiles;
+    total[DEP_G1 * mb + m] = plan[IT_G_L1].n_tiles;
+  }
+  // queue fronts: (m, n) of the next un-emitted item of each kind
+  int fm[6] = {0, 0, 0, 0, 0, 0}, fn[6] = {0, 0, 0, 0, 0, 0};
+  // phase 0: the first row blocks are gathered by all warps of all CTAs before the roles start (one 4-row group per
+  // warp); they need no gather items and their producers finish ~kPhase0Clk after launch
+  const int grid = std::max(1, std::min(P, 1 << 30));
+  const int p0_blocks = std::min(mb, grid * (kPassThreads / 32) / 32);
+  il.phase0_groups = 0;
+  for (int m = 0; m < p0_blocks; ++m) {
+    il.phase0_groups += 32;
+    emitted[DEP_X * mb + m] = total[DEP_X * mb + m];
+    finish[DEP_X * mb + m] = 4000;
+  }
+  fm[IT_GATHER] = p0_blocks;
+  long long remaining = 0;
+  for (int k = 0; k < 6; ++k) if (on[k]) for (int m = (k == IT_GATHER ? p0_blocks : 0); m < mb; ++m) remaining += per_block(k, m);
+  std::vector<uint2> items;
+  items.reserve(remaining + 1);
+  auto push_item = [&](int k, int m, int n) {
+    const int pg = pred_of[k];
+    const unsigned dep_target = pg >= 0 ? static_cast<unsigned>(total[pg * mb + m]) * kEpiWarps : 0u;
+    items.push_back(make_uint2(static_cast<unsigned>(k) | (static_cast<unsigned>(n) << 8) | (dep_target << 16),
+                               static_cast<unsigned>(m)));
+  };
+  if (mb > p0_blocks) {
+    // Large batch: software-pipelined wavefront.  Row blocks are taken in chunks of kWaveBlocks; wave w runs layer 2
+    // of chunk w-3, layer 1 of chunk w-2, layer 0 of chunk w-1 and the gather of chunk w, oldest stage first, so
+    // every tile's inputs were produced a whole wave (thousands of clocks) earlier and dependency waits vanish.
+    constexpr int kWaveBlocks = 16;
+    const int n_chunks = (mb + kWaveBlocks - 1) / kWaveBlocks;
+    static const int stage_of[6] = {1, 1, 2, 2, 3, 0};         // G_L0, D_L0, G_L1, D_L1, G_L2, GATHER
+    static const int order[6] = {IT_G_L2, IT_G_L1, IT_D_L1, IT_G_L0, IT_D_L0, IT_GATHER};
+    for (int wv = 0; wv < n_chunks + 3; ++wv) {
+      for (int oi = 0; oi < 6; ++oi) {
+        const int k = order[oi];
+        if (!on[k]) continue;
+        const int ch = wv - stage_of[k];
+        if (ch < 0 || ch >= n_chunks) continue;
+        for (int m = ch * kWaveBlocks; m < std::min(mb, (ch + 1) * kWaveBlocks); ++m) {
+          if (k == IT_GATHER && m < p0_blocks) continue;
+          for (int n = 0; n < per_block(k, m); ++n) push_item(k, m, n);
+        }
+      }
+    }
+    remaining = 0;
+  }
+  std::vector<long long> free_at(P, 0);
+  // a binary heap would do; P is 148 and the scan is cheap next to the CUDA calls around it
+  while (remaining > 0) {
+    int w = 0;
+    for (int i = 1; i < P; ++i) if (free_at[i] < free_at[w]) w = i;
+    const long long t = free_at[w];
+    int l0_front = mb;  // least row block that still has an un-emitted first-layer tile
+    if (on[IT_G_L0] && fm[IT_G_L0] < mb) l0_front = std::min(l0_front, fm[IT_G_L0]);
+    if (on[IT_D_L0] && fm[IT_D_L0] < mb) l0_front = std::min(l0_front, fm[IT_D_L0]);
+    int best_ready = -1, best_wait = -1, gather_far = -1;
+    long long best_wait_t = 0;
+    for (int k = 0; k < 6; ++k) {
+      if (!on[k] || fm[k] >= mb) continue;
+      const int m = fm[k], pg = pred_of[k];
+      if (pg >= 0 && emitted[pg * mb + m] < total[pg * mb + m]) continue;  // producers not even claimed yet
+      if (k == IT_GATHER && m > l0_front + 48) { gather_far = k; continue; }  // do not front-load every gather
+      const long long rt = pg >= 0 ? finish[pg * mb + m] : 0;
+      if (rt <= t) { if (best_ready < 0 || rank[k] > rank[best_ready]) best_ready = k; }
+      else if (best_wait < 0 || rt < best_wait_t) { best_wait = k; best_wait_t = rt; }
+    }
+    int k = best_ready >= 0 ? best_ready : (best_wait >= 0 ? best_wait : gather_far);
+    if (k < 0) return fail(c, PBG_ERR_INVALID, "internal: work-item scheduler found no candidate");
+    const int m = fm[k], n = fn[k], pg = pred_of[k];
+    const long long rt = pg >= 0 ? finish[pg * mb + m] : 0;
+    const long long start = std::max(t, rt);
+    free_at[w] = start + cost[k];
+    const int og = out_of[k];
+    if (og >= 0) {
+      emitted[og * mb + m] += 1;
+      finish[og * mb + m] = std::max(finish[og * mb + m], start + cost[k] + lat[k]);
+    }
+    const unsigned dep_target = pg >= 0 ? static_cast<unsigned>(total[pg * mb + m]) * kEpiWarps : 0u;
+    items.push_back(make_uint2(static_cast<unsigned>(k) | (static_cast<unsigned>(n) << 8) | (dep_target << 16),
+                               static_cast<unsigned>(m)));
+    if (++fn[k] == per_block(k, m)) { fn[k] = 0; ++fm[k]; }
+    --remaining;
+  }
+  il.n = static_cast<int>(items.size());
+  PBG_CUDA(c, cudaMalloc(&il.dev, sizeof(uint2) * items.size()));
+  PBG_CUDA(c, cudaMemcpy(il.dev, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice));
+  auto ins = c->item_cache.emplace(key, il);
+  *out = &ins.first->second;
+  return PBG_OK;
+}
+
+struct Pass;
+int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
+                void* gen_out, float* scores);
 
 struct Pass {
   const float* node_emb = nullptr; long long N = 0;
@@ -264,9 +461,10 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   gp.xd = a.run_d ? w.xd0 : nullptr; gp.ldd = bf ? c->kd0p : c->kd0;
   gp.B = rows; gp.err_flag = c->err_flag;
   const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
-  { LaunchScope ls(c, PBG_K_GATHER, s);
-    if (bf) gather_concat_kernel<__nv_bfloat16><<<gather_blocks, 256, 0, s>>>(gp);
-    else    gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp); }
+  if (!bf) {  // the bf16 mode gathers inside the fused pass kernel
+    LaunchScope ls(c, PBG_K_GATHER, s);
+    gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp);
+  }
   PBG_CUDA(c, cudaGetLastError());
 
   const size_t out_es = a.out_dtype == PBG_DT_BF16 ? 2 : 4;
@@ -274,30 +472,7 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
 
   if (bf) {
-    if (a.run_g) {
-      GemmParams p{};
-      p.M = (int)rows;
-      p.out = w.bufA; p.ldo = c->hgp; p.n_valid = c->hgp;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_G_L0, c->g[0], w.tm_xg0, p, s));
-      p.out = w.bufB;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_G_L1, c->g[1], w.tm_bufA_g, p, s));
-      GemmParams q{};
-      q.M = (int)rows; q.out = gen_out; q.ldo = E; q.n_valid = E; q.out_f32 = a.out_dtype == PBG_DT_F32;
-      if (scores) {
-        q.cosine = scores; q.tail_tab = a.node_emb; q.n_ent = a.N;
-        q.tail_idx = a.tails + off * a.ts; q.tail_stride = a.ts;
-      }
-      PBG_TRY(launch_gemm<EPI_TANH>(c, PBG_K_G_L2, c->g[2], w.tm_bufB_g, q, s));
-    }
-    if (a.run_d) {
-      GemmParams p{};
-      p.M = (int)rows; p.out = w.bufA; p.ldo = c->hdp; p.n_valid = c->hdp;
-      PBG_TRY(launch_gemm<EPI_LEAKY>(c, PBG_K_D_L0, c->d[0], w.tm_xd0, p, s));
-      GemmParams q{};
-      q.M = (int)rows; q.w3 = c->d_w3_pad; q.b3 = c->d_b3; q.logits = a.logits + off;
-      q.probs = a.probs ? a.probs + off : nullptr;
-      PBG_TRY(launch_gemm<EPI_ROWDOT>(c, PBG_K_D_L1, c->d[1], w.tm_bufA_d, q, s));
-    }
+    return launch_pass(c, w, a, gp, off, rows, gen_out, scores);
   } else {
     float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
     const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
@@ -324,6 +499,61 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
       PBG_CUDA(c, cudaGetLastError());
     }
   }
+  return PBG_OK;
+}
+
+
+int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
+                void* gen_out, float* scores) {
+  ItemList* il = nullptr;
+  PBG_TRY(build_items(c, rows, a.run_g, a.run_d, &il));
+  static bool attr_set = false;
+  static int attr_dev = -1;
+  if (!attr_set || attr_dev != c->dims.device) {
+    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem::kTotal));
+    attr_set = true; attr_dev = c->dims.device;
+  }
+  PassParams p;
+  memset(&p, 0, sizeof p);
+  const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
+  const CUtensorMap* amap[5] = {&w.tm_xg0, &w.tm_xd0, &w.tm_bufA_g, &w.tm_bufD_d, &w.tm_bufB_g};
+  const CUtensorMap* omap[5] = {&w.tmo_bufA, &w.tmo_bufD, &w.tmo_bufB, nullptr, nullptr};
+  const bool on[5] = {a.run_g, a.run_d, a.run_g, a.run_d, a.run_g};
+  static const int pred_of[5] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1};
+  static const int out_of[5] = {DEP_G0, DEP_D0, DEP_G1, -1, -1};
+  static const int epi_of[5] = {PEPI_STORE, PEPI_STORE, PEPI_STORE, PEPI_ROWDOT, PEPI_TANH};
+  __nv_bfloat16* outs[5] = {(__nv_bfloat16*)w.bufA, (__nv_bfloat16*)w.bufD, (__nv_bfloat16*)w.bufB, nullptr, nullptr};
+  const int ldos[5] = {c->hgp, c->hdp, c->hgp, 0, 0};
+  for (int k = 0; k < 5; ++k) {
+    if (!on[k]) continue;
+    const Linear& l = *lin[k];
+    const int bn = il->block_n[k];
+    p.tm_a[k] = *amap[k];
+    p.tm_w[k] = (bn == l.block_n) ? l.tmap_w : l.tmap_w128;
+    if (omap[k]) p.tm_o[k] = *omap[k];
+    p.layer[k] = PassLayer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], ldos[k], 0, l.b_pad, outs[k]};
+    p.layer_mask |= 1u << k;
+  }
+  p.gather = gp;
+  p.phase0_groups = il->phase0_groups;
+  p.items = il->dev; p.n_items = il->n;
+  p.M = static_cast<int>(rows); p.mb_cap = w.mb_cap; p.slope = c->dims.leaky_slope;
+  p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
+  p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
+  if (scores) {
+    p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
+    p.tail_idx = a.tails + off * a.ts; p.tail_stride = a.ts;
+  }
+  p.part_g = w.part_g; p.slots_g = on[IT_G_L2] ? (c->dims.embed_dim + 31) / 32 : 0;  // only the valid columns
+  p.w3 = c->d_w3_pad; p.b3 = c->d_b3;
+  p.logits = a.logits ? a.logits + off : nullptr;
+  p.probs = a.probs ? a.probs + off : nullptr;
+  p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
+  p.trace = c->trace;
+  const int grid = c->num_sms;  // phase 0 and the item order assume one CTA on every SM
+  { LaunchScope ls(c, PBG_K_PASS, a.stream);
+    pbg_pass_kernel<<<grid, kPassThreads, PassSmem::kTotal, a.stream>>>(p); }
+  PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
 
@@ -360,6 +590,8 @@ int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
   *out = nullptr;
   const int E = dims->embed_dim, Z = dims->noise_dim, HG = dims->g_hidden, HD = dims->d_hidden;
   if (E <= 0 || Z <= 0 || HG <= 0 || HD <= 0) return fail(nullptr, PBG_ERR_INVALID, "dims must be positive");
+  if (!(dims->leaky_slope >= 0.f && dims->leaky_slope <= 1.f))
+    return fail(nullptr, PBG_ERR_UNSUPPORTED, "leaky_slope must be in [0, 1]");
   if (E % 8 || Z % 8 || HG % 8 || HD % 16)
     return fail(nullptr, PBG_ERR_UNSUPPORTED, "embed_dim, noise_dim, g_hidden must be multiples of 8 and d_hidden of 16");
   int ndev = 0;
@@ -413,7 +645,8 @@ void pbg_destroy(pbg_ctx* c) {
   for (auto& l : c->d) free_linear(l);
   cudaFree(c->d_w3); cudaFree(c->d_w3_pad);
   free_ws(c->ws_bf16); free_ws(c->ws_f32);
-  cudaFree(c->err_flag);
+  cudaFree(c->err_flag); cudaFree(c->trace);
+  for (auto& kv : c->item_cache) cudaFree(kv.second.dev);
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
   cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
   cudaFree(c->st_logits); cudaFree(c->st_probs);
@@ -558,6 +791,25 @@ int pbg_profile_read(pbg_ctx* c, double* ms, int64_t* count) {
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   c->prof.clear();
+  return PBG_OK;
+}
+
+int pbg_debug_trace(pbg_ctx* c, int enable, int64_t* host_out, int64_t n_slots) {
+  if (!c) return PBG_ERR_INVALID;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  PBG_CUDA(c, cudaDeviceSynchronize());
+  const size_t n = static_cast<size_t>(c->num_sms) * kTraceSlots;
+  if (host_out && c->trace) {
+    std::vector<long long> tmp(n);
+    PBG_CUDA(c, cudaMemcpy(tmp.data(), c->trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n && i < static_cast<size_t>(n_slots); ++i) host_out[i] = tmp[i];
+  }
+  if (enable && !c->trace) {
+    PBG_CUDA(c, cudaMalloc(&c->trace, n * sizeof(long long)));
+  } else if (!enable && c->trace) {
+    cudaFree(c->trace); c->trace = nullptr;
+  }
+  if (c->trace) PBG_CUDA(c, cudaMemset(c->trace, 0, n * sizeof(long long)));
   return PBG_OK;
 }
 

@@ -58,14 +58,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef PBG_HANG_GUARD
 #define PBG_HANG_GUARD 1
 #endif
-// Blocking wait.  With PBG_HANG_GUARD a wait that lasts > ~4 s of SM clock traps instead of
-// hanging the GPU (a protocol bug must never cost a box).
+// Blocking wait.  try_wait suspends the thread in hardware until the phase completes or a time limit expires, so
+// the loop body runs rarely; with PBG_HANG_GUARD a wait that keeps failing for millions of rounds traps instead
+// of hanging the GPU (a protocol bug must never cost a box).  The guard is a register counter: no clock reads.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if PBG_HANG_GUARD
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {
+    if (++spins > 4000000u) {
       printf("pbg: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }

@@ -14,14 +14,14 @@ from . import build as _build
 PBG_OK, PBG_ERR_INVALID, PBG_ERR_CUDA, PBG_ERR_NOT_LOADED, PBG_ERR_INDEX, PBG_ERR_UNSUPPORTED, PBG_ERR_NOMEM = range(7)
 PREC_F32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-KERNEL_KINDS = ("gather", "g_l0", "g_l1", "g_l2", "d_l0", "d_l1", "other")
+KERNEL_KINDS = ("gather", "g_l0", "g_l1", "g_l2", "d_l0", "d_l1", "other", "pass")
 
 # every symbol include/pbg.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
     "pbg_abi_version", "pbg_create", "pbg_destroy", "pbg_last_error", "pbg_load_generator",
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
-    "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_check_indices", "pbg_launch_count",
+    "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
 )
 
 
@@ -67,6 +67,7 @@ def load() -> C.CDLL:
         "pbg_linear_bf16": (C.c_int, [vp, i32, i32, vp, vp, i64, vp]),
         "pbg_profile_enable": (C.c_int, [vp, i32]),
         "pbg_profile_read": (C.c_int, [vp, vp, vp]),
+        "pbg_debug_trace": (C.c_int, [vp, i32, vp, i64]),
         "pbg_check_indices": (C.c_int, [vp, vp]),
         "pbg_launch_count": (i64, [vp]),
     }

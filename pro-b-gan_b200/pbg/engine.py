@@ -122,6 +122,14 @@ class Engine:
         cabi.check(self._lib.pbg_profile_read(self._h, ms, cnt), self._h)
         return {k: (ms[i], cnt[i]) for i, k in enumerate(cabi.KERNEL_KINDS)}
 
+    def debug_trace(self, enable: bool = True):
+        """Read the per-CTA clock64 trace slots ([num_SMs, 256] int64 tensor), then enable / disable tracing and
+        zero the buffer."""
+        n = torch.cuda.get_device_properties(self.device).multi_processor_count * 256
+        buf = (C.c_int64 * n)()
+        cabi.check(self._lib.pbg_debug_trace(self._h, 1 if enable else 0, buf, n), self._h)
+        return torch.tensor(list(buf), dtype=torch.int64).reshape(-1, 256)
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.pbg_launch_count(self._h))
