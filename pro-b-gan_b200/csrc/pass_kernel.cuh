@@ -3,15 +3,17 @@
 //   gather/concat -> G.L0 -> G.L1 -> G.L2 (tanh, cosine)         (pro_b_gan_infer.py:186-188, :201-202)
 //                 -> D.L0 -> D.L1 (+ final H/2 -> 1 dot, sigmoid) (pro_b_gan_infer.py:207, :302)
 //
-// One CTA per SM.  The host cuts the pass into work items (gather units of 32 rows, GEMM tiles of 128 rows x
-// BLOCK_N columns) and orders them so that every item's inputs are produced by earlier items; CTAs claim items
-// in list order from one atomic counter, so any topological order is deadlock-free and the load balances itself.
-// Layers hand activations to each other through L2 (bf16, row-major); a consumer tile waits on a per-(buffer,
-// 128-row block) arrival counter before its first A-operand TMA load -- no grid-wide barrier, no launch per layer.
+// One CTA per SM.  The pass is cut into work items (gather units of 32 rows, GEMM tiles of 128 rows x BLOCK_N
+// columns) that flow through a ready queue in global memory: every (buffer, 128-row block) has an arrival counter,
+// the warp whose arrival completes a block pushes the tiles that consume it, and CTAs pop tickets from the queue.
+// An item is therefore never claimed before its inputs exist -- no CTA sits on an unready tile, nothing depends on
+// which CTAs are resident (several passes can share the GPU from different streams), and the order adapts to the
+// timing it finds.  Layers hand activations to each other through L2 (bf16, row-major): no grid-wide barrier, no
+// launch per layer.
 //
-//   warp 0      scheduler + TMA producer : claims items, publishes them to the CTA through a small smem ring, waits
-//                                          for the item's dependency counter, streams A (128x64) and W (BLOCK_N x 64)
-//                                          boxes into a 4-stage SWIZZLE_128B ring
+//   warp 0      scheduler + TMA producer : pops a ticket, waits for that queue slot to be filled, publishes the item
+//                                          to the CTA through a small smem ring, streams A (128x64) and W (BLOCK_N x
+//                                          64) boxes into a 4-stage SWIZZLE_128B ring
 //   warp 1      MMA issuer              : one thread, tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in
 //                                          TMEM, two accumulator stages of 256 columns
 //   warps 2..9  epilogue (8 warps)      : tcgen05.ld -> bias + activation -> swizzled smem staging -> coalesced
@@ -55,8 +57,11 @@ struct PassLayer {
 };
 
 struct PassSched {
-  int next;  // next unclaimed item
-  int done;  // CTAs that have finished
+  int q_head;   // next pop ticket
+  int q_tail;   // next push slot
+  int p0_next;  // next phase-0 gather group
+  int init;     // 0 -> 1 by the CTA that seeds the queue
+  int done;     // CTAs that have finished
 };
 
 struct alignas(64) PassParams {
@@ -66,9 +71,13 @@ struct alignas(64) PassParams {
   PassLayer layer[5];
   GatherParams gather;
   unsigned layer_mask;  // bit i: layer i takes part in this pass (its tensor maps are valid)
+  int poll_ns;          // back-off between polls of a dependency counter
   int phase0_groups;    // 4-row gather groups done by all warps before the roles start (a multiple of 32 = whole row blocks)
-  const uint2* items;   // x: kind | n_blk << 8 | dep_target << 16 ; y: 128-row block index
-  int n_items;
+  unsigned long long* queue;  // ready queue: (kind + 1) | n_blk << 8 | row block << 32 ; 0 = not pushed yet
+  int n_total;          // items this launch will push (and pop) in total
+  int mb;               // 128-row blocks in this pass
+  int p0_blocks;        // row blocks gathered in phase 0 (phase0_groups / 32)
+  int gather_ahead;     // gather items run this many row blocks ahead of the first-layer tiles
   int M;                // rows in this pass
   int mb_cap;           // stride of the counter arrays (row blocks)
   float slope;
@@ -247,6 +256,61 @@ __device__ __forceinline__ int warp_publish_fetch(int* counter, int lane) {
   return __shfl_sync(0xffffffffu, old, 0);
 }
 
+// ------------------------------------------------------------------------------------------------ ready queue
+__device__ __forceinline__ unsigned long long pass_item(int kind, int n_blk, int m_blk) {
+  return static_cast<unsigned long long>((kind + 1) | (n_blk << 8)) | (static_cast<unsigned long long>(m_blk) << 32);
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int pass_gather_units(const PassParams& p, int m) {
+  const int r = min(kBlockM, p.M - m * kBlockM);
+  return (r + kGatherRows - 1) / kGatherRows;
+}
+__device__ __forceinline__ int pass_dep_target(const PassParams& p, int dep_kind, int m) {
+  if (dep_kind == DEP_X) return m < p.p0_blocks ? 32 : pass_gather_units(p, m) * kEpiWarps;
+  const int producer = dep_kind == DEP_G0 ? IT_G_L0 : (dep_kind == DEP_D0 ? IT_D_L0 : IT_G_L1);
+  return p.layer[producer].n_tiles * kEpiWarps;
+}
+__device__ __forceinline__ void pass_push_gather(const PassParams& p, int m) {
+  const int n = pass_gather_units(p, m);
+  const int base = atomicAdd(&p.sched->q_tail, n);
+  for (int u = 0; u < n; ++u) st_release_gpu_u64(p.queue + base + u, pass_item(IT_GATHER, u, m));
+}
+// One thread, after its arrival completed block m of buffer dep_kind: everything the producers wrote is ordered
+// before the pushes (acquire fence after the completing RMW, release stores into the queue).
+__device__ __forceinline__ void pass_group_done(const PassParams& p, int dep_kind, int m) {
+  fence_acq_rel_gpu();
+  if (dep_kind == DEP_X) {
+    const int ng = (p.layer_mask & (1u << IT_G_L0)) ? p.layer[IT_G_L0].n_tiles : 0;
+    const int nd = (p.layer_mask & (1u << IT_D_L0)) ? p.layer[IT_D_L0].n_tiles : 0;
+    const int base = atomicAdd(&p.sched->q_tail, ng + nd);
+    for (int n = 0; n < ng; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(IT_G_L0, n, m));        // G chain first
+    for (int n = 0; n < nd; ++n) st_release_gpu_u64(p.queue + base + ng + n, pass_item(IT_D_L0, n, m));
+    if (m >= p.p0_blocks && m + p.gather_ahead < p.mb) pass_push_gather(p, m + p.gather_ahead);
+  } else {
+    const int kind = dep_kind == DEP_G0 ? IT_G_L1 : (dep_kind == DEP_D0 ? IT_D_L1 : IT_G_L2);
+    const int nt = p.layer[kind].n_tiles;
+    const int base = atomicAdd(&p.sched->q_tail, nt);
+    for (int n = 0; n < nt; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(kind, n, m));
+  }
+}
+// A warp announces that its part of (dep_kind, m) is in global memory; the arrival that completes the block pushes
+// the block's consumers.  `async_stores`: the data went out through bulk (async-proxy) stores issued by lane 0.
+__device__ __forceinline__ void pass_arrive(const PassParams& p, int dep_kind, int m, int lane, bool async_stores) {
+  __syncwarp();
+  if (lane == 0) {
+    if (async_stores) { tma_store_wait<0>(); fence_proxy_async_all(); }
+    const int old = atom_release_gpu_add(p.ready + dep_kind * p.mb_cap + m, 1);
+    if (old + 1 == pass_dep_target(p, dep_kind, m)) pass_group_done(p, dep_kind, m);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_constant__ PassParams p) {
   using L = PassSmem;
@@ -297,12 +361,19 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
   long long* tr = p.trace ? p.trace + kTraceSlots * blockIdx.x : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); }
 
-  // ---- phase 0: every warp of every CTA gathers one 4-row group of the first row blocks, so that the first-layer
-  // tiles of a small batch wait for one round trip instead of a queue of gather items
-  for (long long g = static_cast<long long>(blockIdx.x) * (kPassThreads / 32) + warp; g < p.phase0_groups;
-       g += static_cast<long long>(gridDim.x) * (kPassThreads / 32)) {
+  // ---- queue seeding: the first CTA to get here pushes the gather items of the first row blocks past phase 0
+  if (threadIdx.x == 0 && p.p0_blocks < p.mb && atomicCAS(&p.sched->init, 0, 1) == 0) {
+    for (int m = p.p0_blocks; m < min(p.mb, p.p0_blocks + p.gather_ahead); ++m) pass_push_gather(p, m);
+  }
+  // ---- phase 0: warps of all CTAs claim 4-row gather groups of the first row blocks, so that the first-layer tiles
+  // of a small batch wait for one index -> row -> store round trip instead of a queue of gather items
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(&p.sched->p0_next, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= p.phase0_groups) break;
     pass_gather_group(p.gather, g, lane);
-    warp_publish(p.ready + DEP_X * p.mb_cap + static_cast<int>(g >> 5), lane);
+    pass_arrive(p, DEP_X, g >> 5, lane, false);
   }
   if (tr && threadIdx.x == 0) tr[5] = clock64();
 
@@ -311,14 +382,26 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
       long long w_dep = 0, w_empty = 0, n_items = 0;
-      auto fetch = [&](int i) -> uint2 { return i < p.n_items ? __ldg(&p.items[i]) : make_uint2(IT_END, 0u); };
-      int i0 = atomicAdd(&p.sched->next, 1);
-      int i1 = atomicAdd(&p.sched->next, 1);
-      uint2 nxt = fetch(i0);
       for (;;) {
-        const uint2 it = nxt;
-        nxt = fetch(i1);                       // descriptor of the item after this one (index known one round ago)
-        i1 = atomicAdd(&p.sched->next, 1);     // claim two ahead; the round trip hides behind this item's loads
+        // pop a ticket (after the previous item's loads are all issued: the MMA still has a full ring to chew on)
+        const int ticket = atomicAdd(&p.sched->q_head, 1);
+        uint2 it = make_uint2(IT_END, 0u);
+        if (ticket < p.n_total) {
+          const long long t = tr ? clock64() : 0;
+          unsigned long long d;
+          uint32_t spins = 0;
+          while ((d = ld_relaxed_gpu_u64(p.queue + ticket)) == 0ull) {
+            __nanosleep(p.poll_ns);
+            if (++spins > 4000000u) { printf("pbg: ready-queue wait timed out (block %d ticket %d)\n", blockIdx.x, ticket); __trap(); }
+          }
+          if (tr) w_dep += clock64() - t;
+          // The item was pushed after its inputs were complete (release stores after an acquire of the block's
+          // counter).  The inputs are read only by TMA (async proxy, from L2), so no generic-proxy acquire fence is
+          // issued -- it would invalidate this SM's L1 (the epilogue's bias lines); the proxy fence orders the
+          // queue read before the bulk loads below.
+          fence_proxy_async_all();
+          it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
+        }
         mbar_wait(&sched_empty[slot], sphase ^ 1);
         ring[slot] = it;
         mbar_arrive(&sched_full[slot]);
@@ -328,9 +411,14 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
         long long* ti = (tr && n_items < kTraceItems) ? tr + 16 + 4 * n_items : nullptr;
         if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; ti[1] = 0; }
         ++n_items;
-        if (kind == IT_GATHER) continue;
+        if (kind == IT_GATHER) {
+          // no loads to issue: wait until the epilogue warps have picked the item up before popping another ticket,
+          // so that an idle scheduler cannot hoard gather items while other CTAs have none
+          const uint32_t used = slot == 0 ? kSchedRing - 1 : slot - 1;
+          mbar_wait(&sched_empty[used], slot == 0 ? sphase ^ 1 : sphase);
+          continue;
+        }
         const int n_blk = (it.x >> 8) & 0xff;
-        const int dep_target = it.x >> 16;
         const int m_blk = static_cast<int>(it.y);
         const PassLayer& ly = p.layer[kind];
         const uint32_t bytes = L::kA + static_cast<uint32_t>(ly.block_n) * kBlockK * 2;
@@ -341,22 +429,6 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
           uint8_t* sb = sa + L::kA;
           mbar_arrive_expect_tx(&full_bar[stage], bytes);
           tma_load_2d(sb, &p.tm_w[kind], &full_bar[stage], kb * kBlockK, n_blk * ly.block_n);  // weights: no dependency
-          if (kb == 0 && dep_target > 0) {
-            const int* ctr = p.ready + ly.dep_kind * p.mb_cap + m_blk;
-            const long long t = tr ? clock64() : 0;
-            uint32_t spins = 0;
-            while (ld_relaxed_gpu(ctr) < dep_target) {
-              __nanosleep(40);
-              if (++spins > 4000000u) { printf("pbg: dependency wait timed out (block %d kind %d m %d)\n", blockIdx.x, kind, m_blk); __trap(); }
-            }
-            if (tr) w_dep += clock64() - t;
-            if (ti) ti[1] = clock64();
-            // The counter was bumped by release-increments that follow the producers' stores (generic proxy) or the
-            // completion of their bulk stores (async proxy).  The tile is read only by TMA (async proxy, from L2), so
-            // no generic-proxy acquire fence is issued -- it would invalidate this SM's L1 (the epilogue's bias
-            // lines) once per tile; the proxy fence orders the flag read before the bulk loads below.
-            fence_proxy_async_all();
-          }
           tma_load_2d(sa, &p.tm_a[kind], &full_bar[stage], kb * kBlockK, m_blk * kBlockM);
           if (++stage == kPassStages) { stage = 0; phase ^= 1; }
         }
@@ -410,25 +482,17 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
     uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     long long w_acc = 0, busy = 0, ph_ld = 0, ph_math = 0, ph_n = 0;
     int item_no = 0;
-    int* pending = nullptr;  // arrival counter of the previous tile: bumped once its TMA stores have completed
+    int pend_kind = -1, pend_m = 0;  // the previous tile's block: announced once its bulk stores have completed
     for (;;) {
+      // Deferred arrival: the previous tile's bulk stores were issued a while ago; waiting for their completion is
+      // cheapest while this warp would idle anyway.  It must not be postponed past a point where the warp blocks on
+      // the ring: the next ring item may be exactly what this arrival releases.
+      if (pend_kind >= 0) { pass_arrive(p, pend_kind, pend_m, lane, true); pend_kind = -1; }
       mbar_wait(&sched_full[slot], sphase);
       const uint2 it = ring[slot];
       __syncwarp();
       if (lane == 0) mbar_arrive(&sched_empty[slot]);
       if (++slot == kSchedRing) { slot = 0; sphase ^= 1; }
-      // Deferred publish: the previous tile's bulk stores were issued a while ago; wait for their completion and
-      // release-increment its counter now, while this warp would otherwise idle waiting for the next accumulator.
-      // (The scheduler publishes an item to the ring before it blocks on anything that item needs, so the flush
-      // can never wait on work that itself waits on the flush.)
-      if (pending != nullptr) {
-        if (lane == 0) {
-          tma_store_wait<0>();
-          fence_proxy_async_all();
-          red_release_gpu_add(pending, 1);
-        }
-        pending = nullptr;
-      }
       const int kind = it.x & 0xff;
       if (kind == IT_END) break;
       const int n_blk = (it.x >> 8) & 0xff;
@@ -438,7 +502,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
       if (kind == IT_GATHER) {
         if (ti) ti[2] = clock64();
         pass_gather_group(p.gather, (static_cast<long long>(m_blk) * kGatherPerBlock + n_blk) * kEpiWarps + wep, lane);
-        warp_publish(p.ready + DEP_X * p.mb_cap + m_blk, lane);
+        pass_arrive(p, DEP_X, m_blk, lane, false);
         if (ti) ti[3] = clock64();
         continue;
       }
@@ -524,7 +588,7 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        pending = p.ready + ly.out_kind * p.mb_cap + m_blk;
+        pend_kind = ly.out_kind; pend_m = m_blk;
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block (deterministic, tile-width independent)
@@ -739,12 +803,12 @@ __global__ void __launch_bounds__(kPassThreads, 1) pbg_pass_kernel(const __grid_
   }
   __syncthreads();
   if (*last_flag) {
-    const int mb = (p.M + kBlockM - 1) / kBlockM;
     for (int k = 0; k < DEP_KINDS; ++k)
-      for (int i = threadIdx.x; i < mb; i += blockDim.x) p.ready[k * p.mb_cap + i] = 0;
+      for (int i = threadIdx.x; i < p.mb; i += blockDim.x) p.ready[k * p.mb_cap + i] = 0;
     for (int k = 0; k < FIN_KINDS; ++k)
-      for (int i = threadIdx.x; i < mb; i += blockDim.x) p.fin[k * p.mb_cap + i] = 0;
-    if (threadIdx.x == 0) { p.sched->next = 0; p.sched->done = 0; }
+      for (int i = threadIdx.x; i < p.mb; i += blockDim.x) p.fin[k * p.mb_cap + i] = 0;
+    for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) p.queue[i] = 0ull;
+    if (threadIdx.x == 0) { p.sched->q_head = 0; p.sched->q_tail = 0; p.sched->p0_next = 0; p.sched->init = 0; p.sched->done = 0; }
     if (tr && threadIdx.x == 0) tr[13] = clock64();
   }
 }

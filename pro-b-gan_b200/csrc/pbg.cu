@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <new>
@@ -61,13 +62,14 @@ struct Workspace {
   PassSched* sched = nullptr;
   float* part_g = nullptr;  // [mb_cap][4][3][128]
   float* part_d = nullptr;  // [mb_cap][2 * max n_tiles][128]
+  unsigned long long* queue = nullptr;  // ready queue, zero between launches
+  long long queue_cap = 0;
 };
 
 struct ItemList {
-  uint2* dev = nullptr;
-  int n = 0;
+  int n = 0;  // work items per launch
   int block_n[5] = {128, 128, 128, 128, 128};
-  int phase0_groups = 0;
+  int phase0_groups = 0, p0_blocks = 0;
 };
 
 thread_local std::string g_create_error;
@@ -164,7 +166,7 @@ void free_linear(Linear& l) {
 
 void free_ws(Workspace& w) {
   cudaFree(w.xg0); cudaFree(w.xd0); cudaFree(w.bufA); cudaFree(w.bufB); cudaFree(w.bufD);
-  cudaFree(w.ready); cudaFree(w.fin); cudaFree(w.sched); cudaFree(w.part_g); cudaFree(w.part_d);
+  cudaFree(w.ready); cudaFree(w.fin); cudaFree(w.sched); cudaFree(w.part_g); cudaFree(w.part_d); cudaFree(w.queue);
   w = Workspace{};
 }
 
@@ -219,6 +221,11 @@ int ensure_ws(pbg_ctx* c, int prec, long long rows) {
     PBG_CUDA(c, cudaMemset(w.ready, 0, sizeof(int) * DEP_KINDS * w.mb_cap));
     PBG_CUDA(c, cudaMemset(w.fin, 0, sizeof(int) * FIN_KINDS * w.mb_cap));
     PBG_CUDA(c, cudaMemset(w.sched, 0, sizeof(PassSched)));
+    // every row block contributes at most: 128-wide tiles of all five layers + 4 gather items
+    w.queue_cap = static_cast<long long>(w.mb_cap) *
+                  (2 * (c->hgp / 128) + c->hdp / 128 + c->hd2p / 128 + c->ep / 128 + kGatherPerBlock) + 64;
+    PBG_CUDA(c, cudaMalloc(&w.queue, sizeof(unsigned long long) * w.queue_cap));
+    PBG_CUDA(c, cudaMemset(w.queue, 0, sizeof(unsigned long long) * w.queue_cap));
     PBG_TRY(make_tmap(c, &w.tm_xg0, w.xg0, cap, c->kg0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_xd0, w.xd0, cap, c->kd0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_bufA_g, w.bufA, cap, c->hgp, kBlockM));
@@ -276,153 +283,46 @@ int launch_f32(pbg_ctx* c, int kind, const Linear& l, const float* A, long long 
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Work-item order of the fused pass kernel.  CTAs claim items in list order, so the list must be a topological
-// order of the dependency graph (gather -> L0 -> L1 -> L2 per 128-row block); which topological order decides how
-// well the tail balances.  The order is produced by list scheduling on a coarse cost model: simulate num_SMs
-// workers, always hand the next free worker the ready item with the longest remaining critical path (or, if none
-// is ready, the one that becomes ready first).  Items of one layer are considered in row-block order, so the
-// candidate set is the front of six queues.
+// Tiling plan of the fused pass kernel for one batch size: tile width per layer, how many row blocks phase 0
+// gathers, and the number of work items the launch will push through its ready queue.
 struct LayerPlan { int num_kb, bn, n_tiles; };
 
-int clk_per_kb(int bn) { return bn >= 256 ? 512 : (bn >= 128 ? 340 : 260); }
+// CTAs per launch of the pass kernel: one per SM unless PBG_GRID asks for fewer (several streams sharing the GPU)
+int pass_grid(const pbg_ctx* c) {
+  static const int env = [] { const char* e = getenv("PBG_GRID"); return e ? atoi(e) : 0; }();
+  return (env > 0 && env < c->num_sms) ? env : c->num_sms;
+}
 
 int build_items(pbg_ctx* c, long long rows, bool run_g, bool run_d, ItemList** out) {
   const auto key = std::make_tuple(rows, static_cast<int>(run_g), static_cast<int>(run_d));
   auto hit = c->item_cache.find(key);
   if (hit != c->item_cache.end()) { *out = &hit->second; return PBG_OK; }
-  if (c->item_cache.size() >= 64) {
-    PBG_CUDA(c, cudaDeviceSynchronize());
-    for (auto& kv : c->item_cache) cudaFree(kv.second.dev);
-    c->item_cache.clear();
-  }
+  if (c->item_cache.size() >= 256) c->item_cache.clear();
   const int mb = static_cast<int>((rows + kBlockM - 1) / kBlockM);
-  const int P = c->num_sms;
+  const int P = pass_grid(c);
   const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
-  const bool on[6] = {run_g, run_d, run_g, run_d, run_g, true};
-  LayerPlan plan[5];
+  const bool on[5] = {run_g, run_d, run_g, run_d, run_g};
   ItemList il;
+  long long total = 0;
   for (int k = 0; k < 5; ++k) {
-    plan[k] = LayerPlan{0, 128, 0};
     if (!on[k]) continue;
     int bn = lin[k]->block_n;
     if (bn == 256 && static_cast<long long>(mb) * (lin[k]->np / 256) < P / 2) bn = 128;  // small batch: finer tiles
-    plan[k] = LayerPlan{lin[k]->kp / kBlockK, bn, lin[k]->np / bn};
     il.block_n[k] = bn;
-    if (plan[k].n_tiles > 255) return fail(c, PBG_ERR_UNSUPPORTED, "layer too wide for the tile index");
+    if (lin[k]->np / bn > 255) return fail(c, PBG_ERR_UNSUPPORTED, "layer too wide for the tile index");
+    total += static_cast<long long>(mb) * (lin[k]->np / bn);
   }
   if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 32 > kPartSlotsG) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
-
-  static const int pred_of[6] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1, -1};
-  static const int out_of[6] = {DEP_G0, DEP_D0, DEP_G1, -1, -1, DEP_X};
-  auto units_of = [&](int m) {
+  // phase 0: the first row blocks are gathered by all warps before the roles start, one 4-row group per warp and
+  // round; the rest of the batch goes through gather items (32 rows each)
+  il.p0_blocks = std::min(mb, P * (kPassThreads / 32) / 32);
+  il.phase0_groups = il.p0_blocks * 32;
+  for (int m = il.p0_blocks; m < mb; ++m) {
     const long long r = std::min<long long>(kBlockM, rows - static_cast<long long>(m) * kBlockM);
-    return static_cast<int>((r + kGatherRows - 1) / kGatherRows);
-  };
-  auto per_block = [&](int kind, int m) { return kind == IT_GATHER ? units_of(m) : plan[kind].n_tiles; };
-  long long cost[6], lat[6], rank[6];
-  for (int k = 0; k < 5; ++k) { cost[k] = static_cast<long long>(plan[k].num_kb) * clk_per_kb(plan[k].bn) + 300; lat[k] = 1500; }
-  cost[IT_GATHER] = 1200; lat[IT_GATHER] = 5000;
-  rank[IT_G_L2] = cost[IT_G_L2];
-  rank[IT_G_L1] = cost[IT_G_L1] + lat[IT_G_L1] + rank[IT_G_L2];
-  rank[IT_G_L0] = cost[IT_G_L0] + lat[IT_G_L0] + rank[IT_G_L1];
-  rank[IT_D_L1] = cost[IT_D_L1];
-  rank[IT_D_L0] = cost[IT_D_L0] + lat[IT_D_L0] + rank[IT_D_L1];
-  rank[IT_GATHER] = 1LL << 40;
-
-  std::vector<int> emitted(DEP_KINDS * mb, 0), total(DEP_KINDS * mb, 0);
-  std::vector<long long> finish(DEP_KINDS * mb, 0);
-  for (int m = 0; m < mb; ++m) {
-    total[DEP_X * mb + m] = units_of(m);
-    total[DEP_G0 * mb + m] = plan[IT_G_L0].n_tiles;
-    total[DEP_D0 * mb + m] = plan[IT_D_L0].n_tiles;
-    total[DEP_G1 * mb + m] = plan[IT_G_L1].n_tiles;
+    total += (r + kGatherRows - 1) / kGatherRows;
   }
-  // queue fronts: (m, n) of the next un-emitted item of each kind
-  int fm[6] = {0, 0, 0, 0, 0, 0}, fn[6] = {0, 0, 0, 0, 0, 0};
-  // phase 0: the first row blocks are gathered by all warps of all CTAs before the roles start (one 4-row group per
-  // warp); they need no gather items and their producers finish ~kPhase0Clk after launch
-  const int grid = std::max(1, std::min(P, 1 << 30));
-  const int p0_blocks = std::min(mb, grid * (kPassThreads / 32) / 32);
-  il.phase0_groups = 0;
-  for (int m = 0; m < p0_blocks; ++m) {
-    il.phase0_groups += 32;
-    emitted[DEP_X * mb + m] = total[DEP_X * mb + m];
-    finish[DEP_X * mb + m] = 4000;
-  }
-  fm[IT_GATHER] = p0_blocks;
-  long long remaining = 0;
-  for (int k = 0; k < 6; ++k) if (on[k]) for (int m = (k == IT_GATHER ? p0_blocks : 0); m < mb; ++m) remaining += per_block(k, m);
-  std::vector<uint2> items;
-  items.reserve(remaining + 1);
-  auto push_item = [&](int k, int m, int n) {
-    const int pg = pred_of[k];
-    const unsigned dep_target = pg >= 0 ? static_cast<unsigned>(total[pg * mb + m]) * kEpiWarps : 0u;
-    items.push_back(make_uint2(static_cast<unsigned>(k) | (static_cast<unsigned>(n) << 8) | (dep_target << 16),
-                               static_cast<unsigned>(m)));
-  };
-  if (mb > p0_blocks) {
-    // Large batch: software-pipelined wavefront.  Row blocks are taken in chunks of kWaveBlocks; wave w runs layer 2
-    // of chunk w-3, layer 1 of chunk w-2, layer 0 of chunk w-1 and the gather of chunk w, oldest stage first, so
-    // every tile's inputs were produced a whole wave (thousands of clocks) earlier and dependency waits vanish.
-    constexpr int kWaveBlocks = 16;
-    const int n_chunks = (mb + kWaveBlocks - 1) / kWaveBlocks;
-    static const int stage_of[6] = {1, 1, 2, 2, 3, 0};         // G_L0, D_L0, G_L1, D_L1, G_L2, GATHER
-    static const int order[6] = {IT_G_L2, IT_G_L1, IT_D_L1, IT_G_L0, IT_D_L0, IT_GATHER};
-    for (int wv = 0; wv < n_chunks + 3; ++wv) {
-      for (int oi = 0; oi < 6; ++oi) {
-        const int k = order[oi];
-        if (!on[k]) continue;
-        const int ch = wv - stage_of[k];
-        if (ch < 0 || ch >= n_chunks) continue;
-        for (int m = ch * kWaveBlocks; m < std::min(mb, (ch + 1) * kWaveBlocks); ++m) {
-          if (k == IT_GATHER && m < p0_blocks) continue;
-          for (int n = 0; n < per_block(k, m); ++n) push_item(k, m, n);
-        }
-      }
-    }
-    remaining = 0;
-  }
-  std::vector<long long> free_at(P, 0);
-  // a binary heap would do; P is 148 and the scan is cheap next to the CUDA calls around it
-  while (remaining > 0) {
-    int w = 0;
-    for (int i = 1; i < P; ++i) if (free_at[i] < free_at[w]) w = i;
-    const long long t = free_at[w];
-    int l0_front = mb;  // least row block that still has an un-emitted first-layer tile
-    if (on[IT_G_L0] && fm[IT_G_L0] < mb) l0_front = std::min(l0_front, fm[IT_G_L0]);
-    if (on[IT_D_L0] && fm[IT_D_L0] < mb) l0_front = std::min(l0_front, fm[IT_D_L0]);
-    int best_ready = -1, best_wait = -1, gather_far = -1;
-    long long best_wait_t = 0;
-    for (int k = 0; k < 6; ++k) {
-      if (!on[k] || fm[k] >= mb) continue;
-      const int m = fm[k], pg = pred_of[k];
-      if (pg >= 0 && emitted[pg * mb + m] < total[pg * mb + m]) continue;  // producers not even claimed yet
-      if (k == IT_GATHER && m > l0_front + 48) { gather_far = k; continue; }  // do not front-load every gather
-      const long long rt = pg >= 0 ? finish[pg * mb + m] : 0;
-      if (rt <= t) { if (best_ready < 0 || rank[k] > rank[best_ready]) best_ready = k; }
-      else if (best_wait < 0 || rt < best_wait_t) { best_wait = k; best_wait_t = rt; }
-    }
-    int k = best_ready >= 0 ? best_ready : (best_wait >= 0 ? best_wait : gather_far);
-    if (k < 0) return fail(c, PBG_ERR_INVALID, "internal: work-item scheduler found no candidate");
-    const int m = fm[k], n = fn[k], pg = pred_of[k];
-    const long long rt = pg >= 0 ? finish[pg * mb + m] : 0;
-    const long long start = std::max(t, rt);
-    free_at[w] = start + cost[k];
-    const int og = out_of[k];
-    if (og >= 0) {
-      emitted[og * mb + m] += 1;
-      finish[og * mb + m] = std::max(finish[og * mb + m], start + cost[k] + lat[k]);
-    }
-    const unsigned dep_target = pg >= 0 ? static_cast<unsigned>(total[pg * mb + m]) * kEpiWarps : 0u;
-    items.push_back(make_uint2(static_cast<unsigned>(k) | (static_cast<unsigned>(n) << 8) | (dep_target << 16),
-                               static_cast<unsigned>(m)));
-    if (++fn[k] == per_block(k, m)) { fn[k] = 0; ++fm[k]; }
-    --remaining;
-  }
-  il.n = static_cast<int>(items.size());
-  PBG_CUDA(c, cudaMalloc(&il.dev, sizeof(uint2) * items.size()));
-  PBG_CUDA(c, cudaMemcpy(il.dev, items.data(), sizeof(uint2) * items.size(), cudaMemcpyHostToDevice));
+  il.n = static_cast<int>(total);
   auto ins = c->item_cache.emplace(key, il);
   *out = &ins.first->second;
   return PBG_OK;
@@ -535,8 +435,12 @@ int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp,
     p.layer_mask |= 1u << k;
   }
   p.gather = gp;
-  p.phase0_groups = il->phase0_groups;
-  p.items = il->dev; p.n_items = il->n;
+  static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
+  p.poll_ns = poll_env;
+  p.phase0_groups = il->phase0_groups; p.p0_blocks = il->p0_blocks; p.gather_ahead = 32;
+  p.mb = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+  p.queue = w.queue; p.n_total = il->n;
+  if (il->n > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
   p.M = static_cast<int>(rows); p.mb_cap = w.mb_cap; p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
@@ -550,7 +454,7 @@ int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp,
   p.probs = a.probs ? a.probs + off : nullptr;
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
-  const int grid = c->num_sms;  // phase 0 and the item order assume one CTA on every SM
+  const int grid = pass_grid(c);  // phase 0 and the item order assume this many co-resident CTAs
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
     pbg_pass_kernel<<<grid, kPassThreads, PassSmem::kTotal, a.stream>>>(p); }
   PBG_CUDA(c, cudaGetLastError());
@@ -646,7 +550,7 @@ void pbg_destroy(pbg_ctx* c) {
   cudaFree(c->d_w3); cudaFree(c->d_w3_pad);
   free_ws(c->ws_bf16); free_ws(c->ws_f32);
   cudaFree(c->err_flag); cudaFree(c->trace);
-  for (auto& kv : c->item_cache) cudaFree(kv.second.dev);
+
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
   cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
   cudaFree(c->st_logits); cudaFree(c->st_probs);
