@@ -1,0 +1,657 @@
+// pass2_kernel.cuh -- the generator + discriminator pass as ONE persistent kernel of CTA PAIRS (cta_group::2).
+//
+//   gather/concat -> G.L0 -> G.L1 -> G.L2 (tanh, cosine)         (pro_b_gan_infer.py:186-188, :201-202)
+//                 -> D.L0 -> D.L1 (+ final H/2 -> 1 dot, sigmoid) (pro_b_gan_infer.py:207, :302)
+//
+// Same data flow as pass_kernel.cuh (work items through a ready queue in global memory, activations handed from
+// layer to layer through L2, per-row-block arrival counters), re-cut for the L2 -> SM operand bandwidth that bounds
+// it: two CTAs on one TPC form a pair and compute one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2
+// (M = 256: 128 rows of A per CTA; the BLOCK_N rows of W are split in halves, one per CTA), so a 64-deep k-block
+// costs each SM 16 KB of A + 16 KB of W (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for a single-CTA
+// 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).
+//
+//   leader CTA (cluster rank 0)                               peer CTA (rank 1)
+//   warp 0   scheduler: pops tickets, publishes items to      warp 0   TMA producer for its halves of A and W,
+//            both CTAs' rings; TMA producer for its halves             signalling the leader's full barriers
+//   warp 1   MMA issuer (one thread) for the pair             warp 1   idle
+//   warps 2..9  epilogue of its 128 rows / gather items       warps 2..9  epilogue of its 128 rows / gather items
+//
+// Epilogues: bias + LeakyReLU -> bf16 -> swizzled staging (double-buffered per warp) -> TMA store; the final
+// discriminator dot and the cosine against the tail embedding are written as per-64-column partials that the last
+// warp to arrive for the 256-row block sums in a fixed order (bit-identical for any batch size / interleaving).
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+#include "gather.cuh"
+#include "gemm_tc.cuh"
+#include "pass_kernel.cuh"
+
+namespace pbg {
+
+constexpr int kP2Stages = 5;
+constexpr int kP2Ring = 4;
+constexpr int kP2Rows = 256;                        // rows of one pair tile = one dependency block
+constexpr int kP2GroupsPerBlock = kP2Rows / 4;      // 4-row gather groups per block
+constexpr int kP2GatherPerBlock = 4;                // gather items per block: 64 rows = 16 warps x 4 rows
+constexpr int kP2WarpsPerPair = 2 * kEpiWarps;
+
+struct P2Layer {
+  int num_kb;        // K / 64
+  int block_n;       // UMMA N of this layer's pair tiles (128 / 256)
+  int n_tiles;       // padded output width / block_n
+  int epi;           // PEPI_*
+  int dep_kind;      // DEP_* counter that gates this layer's A operand
+  int out_kind;      // DEP_* counter this layer's stores bump, or -1
+  const float* bias; // [n_tiles * block_n] fp32, zero padded
+};
+
+struct alignas(64) Pass2Params {
+  CUtensorMap tm_a[5];  // A operand of layer i: xg0, xd0, actG0, actD0, actG1   (box 64 x 128 rows, SWIZZLE_128B)
+  CUtensorMap tm_w[5];  // weights of layer i                                      (box 64 x block_n / 2 rows)
+  CUtensorMap tm_o[5];  // PEPI_STORE layers: the activation buffer they write      (box 64 x 32 rows)
+  P2Layer layer[5];
+  GatherParams gather;
+  unsigned layer_mask;
+  int poll_ns;
+  int phase0_groups;    // 4-row gather groups done by the epilogue warps of all CTAs before the roles start
+  int p0_blocks;        // = phase0_groups / 64
+  int gather_ahead;     // gather items run this many row blocks ahead of the first-layer tiles
+  int n_total;          // items this launch pushes (and pops) in total
+  int nrb;              // 256-row blocks in this pass
+  int rb_cap;           // stride of the counter arrays
+  int M;                // rows in this pass
+  float slope;
+  unsigned long long* queue;
+  PassSched* sched;
+  int* ready;           // [DEP_KINDS][rb_cap]
+  int* fin;             // [FIN_KINDS][rb_cap]
+  // generator output (PEPI_TANH)
+  void* gen_out; int out_f32; int n_valid; int ld_gen;
+  float* cosine; const float* tail_tab; const long long* tail_idx; long long tail_stride; long long n_ent;
+  float* part_g;        // [nrb][slots_g][3][256]
+  int slots_g;
+  // discriminator output (PEPI_ROWDOT)
+  const float* w3; float b3; float* logits; float* probs;
+  float* part_d;        // [nrb][slots_d][256]
+  int slots_d;
+  long long* trace;
+};
+
+struct P2Smem {
+  static constexpr int kA = 128 * kBlockK * 2;
+  static constexpr int kW = 128 * kBlockK * 2;   // this CTA's half of a 256-wide W tile
+  static constexpr int kStage = kA + kW;
+  static constexpr int kStagingOff = kP2Stages * kStage;
+  static constexpr int kStagingPerWarp = 8192;   // two 4 KB store tiles / one 32 x 64 fp32 transpose tile
+  static constexpr int kBarOff = kStagingOff + kEpiWarps * kStagingPerWarp;
+  static constexpr int kTotal = kBarOff + 512 + 1024 /*alignment slack*/;
+};
+static_assert(P2Smem::kTotal <= 232448, "pass2: shared memory budget");
+
+__device__ __forceinline__ void st_cluster_u32x2(uint32_t cluster_addr, uint2 v) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// bf16x2( leaky(a + b) ): packed fp32 add and multiply, scalar max, one packed convert
+__device__ __forceinline__ uint32_t bias_leaky_pack(uint32_t a0, uint32_t a1, float b0, float b1, float slope) {
+  const float2 y = add2(make_float2(__uint_as_float(a0), __uint_as_float(a1)), make_float2(b0, b1));
+  const float2 s = mul2(y, make_float2(slope, slope));
+  return pack_bf16x2(fmaxf(y.x, s.x), fmaxf(y.y, s.y));
+}
+
+__device__ __forceinline__ int p2_dep_target(const Pass2Params& p, int dep_kind) {
+  if (dep_kind == DEP_X) return kP2GroupsPerBlock;
+  const int producer = dep_kind == DEP_G0 ? IT_G_L0 : (dep_kind == DEP_D0 ? IT_D_L0 : IT_G_L1);
+  return p.layer[producer].n_tiles * kP2WarpsPerPair;
+}
+__device__ __forceinline__ void p2_push_gather(const Pass2Params& p, int rb) {
+  const int base = atomicAdd(&p.sched->q_tail, kP2GatherPerBlock);
+  for (int u = 0; u < kP2GatherPerBlock; ++u) st_release_gpu_u64(p.queue + base + u, pass_item(IT_GATHER, u, rb));
+}
+// One thread, after its arrival completed block rb of buffer dep_kind: push the block's consumers.
+__device__ __forceinline__ void p2_group_done(const Pass2Params& p, int dep_kind, int rb) {
+  fence_acq_rel_gpu();
+  if (dep_kind == DEP_X) {
+    const int ng = (p.layer_mask & (1u << IT_G_L0)) ? p.layer[IT_G_L0].n_tiles : 0;
+    const int nd = (p.layer_mask & (1u << IT_D_L0)) ? p.layer[IT_D_L0].n_tiles : 0;
+    const int base = atomicAdd(&p.sched->q_tail, ng + nd);
+    for (int n = 0; n < ng; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(IT_G_L0, n, rb));
+    for (int n = 0; n < nd; ++n) st_release_gpu_u64(p.queue + base + ng + n, pass_item(IT_D_L0, n, rb));
+    if (rb >= p.p0_blocks && rb + p.gather_ahead < p.nrb) p2_push_gather(p, rb + p.gather_ahead);
+  } else {
+    const int kind = dep_kind == DEP_G0 ? IT_G_L1 : (dep_kind == DEP_D0 ? IT_D_L1 : IT_G_L2);
+    const int nt = p.layer[kind].n_tiles;
+    const int base = atomicAdd(&p.sched->q_tail, nt);
+    for (int n = 0; n < nt; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(kind, n, rb));
+  }
+}
+__device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, int rb, int lane, bool async_stores) {
+  __syncwarp();
+  if (lane == 0) {
+    if (async_stores) { tma_store_wait<0>(); fence_proxy_async_all(); }
+    const int old = atom_release_gpu_add(p.ready + dep_kind * p.rb_cap + rb, 1);
+    if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
+  using L = P2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kP2Stages;
+  uint64_t* tmem_full = empty_bar + kP2Stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* sched_full = tmem_empty + 2;
+  uint64_t* sched_empty = sched_full + kP2Ring;
+  uint2* ring = reinterpret_cast<uint2*>(sched_empty + kP2Ring);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + kP2Ring);
+  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) {
+      if (p.layer_mask & (1u << i)) {
+        prefetch_tmap(&p.tm_a[i]);
+        prefetch_tmap(&p.tm_w[i]);
+        if (p.layer[i].epi == PEPI_STORE) prefetch_tmap(&p.tm_o[i]);
+      }
+    }
+    for (int s = 0; s < kP2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);     // leader's: its producer's arrive.expect_tx (bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);    // tcgen05.commit, multicast to both CTAs
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);                  // tcgen05.commit, multicast
+      mbar_init(&tmem_empty[s], kP2WarpsPerPair);   // leader's: the epilogue warps of both CTAs
+    }
+    for (int s = 0; s < kP2Ring; ++s) {
+      mbar_init(&sched_full[s], 1);                       // the leader's scheduler (local + remote arrive)
+      mbar_init(&sched_empty[s], 2 * (1 + kEpiWarps));    // leader's: {MMA | peer producer} + 8 epilogue warps, per CTA
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long* tr = p.trace ? p.trace + kTraceSlots * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); }
+
+  // addresses of the leader's barriers as seen from either CTA
+  const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);
+  const uint32_t lead_sched_empty = mapa_u32(smem_u32(sched_empty), 0);
+
+  // ---- queue seeding: gather items of the first row blocks past phase 0
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int rb = p.p0_blocks; rb < min(p.nrb, p.p0_blocks + p.gather_ahead); ++rb) p2_push_gather(p, rb);
+  }
+  // ---- phase 0: the epilogue warps of all CTAs gather the first row blocks, one 4-row group per warp and round
+  //      (static assignment: no claim atomics); warps 0 / 1 go straight to their roles
+  if (warp >= 2) {
+    const int gw = static_cast<int>(blockIdx.x) * kEpiWarps + (warp - 2);
+    const int gstep = static_cast<int>(gridDim.x) * kEpiWarps;
+    for (int g = gw; g < p.phase0_groups; g += gstep) {
+      pass_gather_group(p.gather, g, lane);
+      p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
+    }
+    if (tr && threadIdx.x == 64) tr[5] = clock64();
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ scheduler (leader) + TMA producer (both)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
+      long long w_dep = 0, w_empty = 0, n_items = 0;
+      const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
+      const uint32_t peer_ring = mapa_u32(smem_u32(ring), 1);
+      const uint32_t peer_sched_full = mapa_u32(smem_u32(sched_full), 1);
+      for (;;) {
+        uint2 it;
+        if (leader) {
+          const int ticket = atomicAdd(&p.sched->q_head, 1);
+          it = make_uint2(IT_END, 0u);
+          if (ticket < p.n_total) {
+            const long long t = tr ? clock64() : 0;
+            unsigned long long d;
+            uint32_t spins = 0;
+            while ((d = ld_relaxed_gpu_u64(p.queue + ticket)) == 0ull) {
+              __nanosleep(p.poll_ns);
+              if (++spins > 4000000u) { printf("pbg: ready-queue wait timed out (block %d ticket %d of %d)\n", blockIdx.x, ticket, p.n_total); __trap(); }
+            }
+            if (tr) w_dep += clock64() - t;
+            it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
+          }
+          mbar_wait_cluster(&sched_empty[slot], sphase ^ 1);
+          ring[slot] = it;
+          st_cluster_u32x2(peer_ring + slot * 8, it);
+          mbar_arrive(&sched_full[slot]);
+          mbar_arrive_cluster(peer_sched_full + slot * 8);
+        } else {
+          mbar_wait_cluster(&sched_full[slot], sphase);
+          it = ring[slot];
+          mbar_arrive_cluster(lead_sched_empty + slot * 8);
+        }
+        // the item's inputs were complete before it was pushed; they are read by TMA only (async proxy, from L2)
+        fence_proxy_async_all();
+        const uint32_t used = slot;
+        const uint32_t used_phase = sphase;
+        if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+        const int kind = it.x & 0xff;
+        if (kind == IT_END) break;
+        long long* ti = (tr && n_items < kTraceItems) ? tr + 16 + 4 * n_items : nullptr;
+        if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; ti[1] = 0; }
+        ++n_items;
+        if (kind == IT_GATHER) {
+          // no loads to issue: wait until everybody has picked the item up before popping another ticket, so that
+          // an idle scheduler cannot hoard gather items while other pairs have none
+          if (leader) mbar_wait_cluster(&sched_empty[used], used_phase);
+          continue;
+        }
+        const int n_blk = (it.x >> 8) & 0xff;
+        const int rb = static_cast<int>(it.y);
+        const P2Layer& ly = p.layer[kind];
+        const int w_rows = ly.block_n >> 1;
+        const uint32_t bytes_pair = 2u * (L::kA + static_cast<uint32_t>(w_rows) * kBlockK * 2);
+        const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
+        const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
+        for (int kb = 0; kb < ly.num_kb; ++kb) {
+          if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
+          else mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStage;
+          uint8_t* sb = sa + L::kA;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
+          tma_load_2d_pair(sb, &p.tm_w[kind], lead_full + stage * 8, kb * kBlockK, w_row);
+          tma_load_2d_pair(sa, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
+          if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (tr) { tr[1] = w_empty; tr[2] = clock64(); tr[11] = w_dep; tr[12] = n_items; }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader only)
+    if (leader && lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
+      long long w_full = 0, w_tmem = 0, n_kb = 0;
+      for (;;) {
+        mbar_wait(&sched_full[slot], sphase);
+        const uint2 it = ring[slot];
+        mbar_arrive(&sched_empty[slot]);
+        if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+        const int kind = it.x & 0xff;
+        if (kind == IT_END) break;
+        if (kind == IT_GATHER) continue;
+        const P2Layer& ly = p.layer[kind];
+        const uint32_t idesc = make_idesc_bf16(kP2Rows, static_cast<uint32_t>(ly.block_n));
+        if (tr) { const long long t = clock64(); mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
+        else mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < ly.num_kb; ++kb) {
+          if (tr) { const long long t = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - t; ++n_kb; }
+          else mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStage);
+          const uint64_t da = make_kmajor_sw128_desc(sa);
+          const uint64_t db = make_kmajor_sw128_desc(sa + L::kA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[acc], 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue + gather warps (both CTAs)
+    const int wep = warp - 2;          // 0..7
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = wep >> 2;         // which half of a tile's 64-column chunks this warp takes
+    uint8_t* st = smem + L::kStagingOff + wep * L::kStagingPerWarp;
+    uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0, buf = 0;
+    long long w_acc = 0, busy = 0, ph_ld = 0, ph_math = 0, ph_n = 0;
+    int item_no = 0;
+    int pend_kind = -1, pend_rb = 0;   // previous tile's block: announced once its bulk stores have completed
+    const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
+    for (;;) {
+      if (pend_kind >= 0) { p2_arrive(p, pend_kind, pend_rb, lane, true); pend_kind = -1; }
+      if (leader) mbar_wait(&sched_full[slot], sphase); else mbar_wait_cluster(&sched_full[slot], sphase);
+      const uint2 it = ring[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_sched_empty + slot * 8);
+      if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+      const int kind = it.x & 0xff;
+      if (kind == IT_END) break;
+      const int n_blk = (it.x >> 8) & 0xff;
+      const int rb = static_cast<int>(it.y);
+      long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
+      ++item_no;
+      if (kind == IT_GATHER) {
+        if (ti) ti[2] = clock64();
+        pass_gather_group(p.gather, static_cast<long long>(rb) * kP2GroupsPerBlock + n_blk * kP2WarpsPerPair + rank * kEpiWarps + wep, lane);
+        p2_arrive(p, DEP_X, rb, lane, false);
+        if (ti) ti[3] = clock64();
+        continue;
+      }
+      const P2Layer& ly = p.layer[kind];
+      const long long grow = static_cast<long long>(rb) * kP2Rows + row_in_blk;
+      const bool row_ok = grow < p.M;
+      const int n0 = n_blk * ly.block_n;
+      const int n_chunks = ly.block_n >> 6;   // 64-column chunks per tile; this warp takes c = half, half + 2, ...
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+
+      // PEPI_TANH prefetch (before the accumulator wait): tail index and the tail row pieces of the first chunk
+      const bool want_cos = ly.epi == PEPI_TANH && p.cosine != nullptr;
+      unsigned long long trow_bits = 0ull;
+      float4 tv[16];
+      if (want_cos) {
+        const float* trow = nullptr;
+        if (row_ok) {
+          long long tid = p.tail_idx[grow * p.tail_stride];
+          tid = (tid < 0 || tid >= p.n_ent) ? 0 : tid;  // the gather has already flagged it
+          trow = p.tail_tab + tid * p.n_valid;
+        }
+        trow_bits = reinterpret_cast<unsigned long long>(trow);
+        if (half < n_chunks) {
+          const int col0 = n0 + half * 64;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = i * 2 + (lane >> 4), t = lane & 15;
+            const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
+            tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp2 != nullptr && col0 + t * 4 < p.n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
+          }
+        }
+      }
+      {
+        const long long t = (tr && lane == 0) ? clock64() : 0;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        if (tr && lane == 0) { w_acc += clock64() - t; }
+        if (ti) ti[2] = clock64();
+      }
+      const long long t_busy0 = (tr && lane == 0) ? clock64() : 0;
+      tc_fence_after();
+
+      if (ly.epi == PEPI_STORE) {
+        // ---- bias + LeakyReLU -> bf16 -> swizzled staging tile -> one TMA store per 32-row x 64-column chunk
+        const bool tp = tr && threadIdx.x == 64;
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        const float slope = p.slope;
+        const float* const bias_tile = ly.bias + n0;
+        const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
+        for (int c = half; c < n_chunks; c += 2) {
+          if (tp) tq0 = clock64();
+          const float4* b4 = reinterpret_cast<const float4*>(bias_tile + c * 64);
+          uint32_t v[64];
+          tmem_ld_32x32_ptr(taddr + c * 64, v);
+          tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
+          // this staging buffer is free once the bulk store issued two chunks ago has read it
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sbuf = st + buf * 4096;
+          tmem_ld_wait();
+          if (c + 2 >= n_chunks) {  // this warp's last read of the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          }
+          if (tp) tq1 = clock64();
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float4 ba = __ldg(b4 + 2 * t), bb = __ldg(b4 + 2 * t + 1);
+            uint4 w;
+            w.x = bias_leaky_pack(v[8 * t + 0], v[8 * t + 1], ba.x, ba.y, slope);
+            w.y = bias_leaky_pack(v[8 * t + 2], v[8 * t + 3], ba.z, ba.w, slope);
+            w.z = bias_leaky_pack(v[8 * t + 4], v[8 * t + 5], bb.x, bb.y, slope);
+            w.w = bias_leaky_pack(v[8 * t + 6], v[8 * t + 7], bb.z, bb.w, slope);
+            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
+          }
+          fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
+            tma_store_commit();
+          }
+          buf ^= 1;
+          if (tp) { tq2 = clock64(); ph_ld += tq1 - tq0; ph_math += tq2 - tq1; ph_n += 1; }
+        }
+        if (half >= n_chunks) {  // narrow tile: this warp had no chunk, still has to release the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+        }
+        pend_kind = ly.out_kind; pend_rb = rb;
+      } else if (ly.epi == PEPI_ROWDOT) {
+        // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
+        //      fixed order by the last warp to arrive for this row block
+        const float slope = p.slope;
+        float* part = p.part_d + (static_cast<size_t>(rb) * p.slots_d) * kP2Rows;
+        for (int c = half; c < n_chunks; c += 2) {
+          uint32_t v[64];
+          tmem_ld_32x32_ptr(taddr + c * 64, v);
+          tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
+          const float4* b4 = reinterpret_cast<const float4*>(ly.bias + n0 + c * 64);
+          const float4* w4 = reinterpret_cast<const float4*>(p.w3 + n0 + c * 64);
+          tmem_ld_wait();
+          if (c + 2 >= n_chunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          }
+          float rowdot = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j), w = __ldg(w4 + j);
+            rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 0]) + b.x, slope), w.x, rowdot);
+            rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 1]) + b.y, slope), w.y, rowdot);
+            rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 2]) + b.z, slope), w.z, rowdot);
+            rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 3]) + b.w, slope), w.w, rowdot);
+          }
+          part[((n0 >> 6) + c) * kP2Rows + row_in_blk] = rowdot;
+        }
+        if (half >= n_chunks) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+        }
+        const int old = warp_publish_fetch(p.fin + FIN_D * p.rb_cap + rb, lane);
+        if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
+          fence_acq_rel_gpu();
+          __syncwarp();
+          for (int r = lane; r < kP2Rows; r += 32) {
+            const long long gr = static_cast<long long>(rb) * kP2Rows + r;
+            float s = 0.f;
+            for (int k = 0; k < p.slots_d; ++k) s += __ldcg(part + k * kP2Rows + r);
+            if (gr < p.M) {
+              const float logit = s + p.b3;
+              p.logits[gr] = logit;
+              if (p.probs != nullptr) p.probs[gr] = 1.f / (1.f + __expf(-logit));
+            }
+          }
+        }
+      } else {
+        // ---- PEPI_TANH: bias + tanh -> generator output (fp32 / bf16), optional cosine vs the tail embedding
+        const bool want_out = p.gen_out != nullptr;
+        float* part = p.part_g + (static_cast<size_t>(rb) * p.slots_g) * 3 * kP2Rows;
+        // the staging tile may still be the source of an activation store issued by an earlier tile of this warp
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        for (int c = half; c < n_chunks; c += 2) {
+          const int col0 = n0 + c * 64;
+          uint32_t v[64];
+          tmem_ld_32x32_ptr(taddr + c * 64, v);
+          tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
+          if (want_cos && c != half) {  // later chunks of a wide tile: fetch their tail pieces now
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = i * 2 + (lane >> 4), t = lane & 15;
+              const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
+              tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (tp2 != nullptr && col0 + t * 4 < p.n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
+            }
+          }
+          const float4* b4 = reinterpret_cast<const float4*>(ly.bias + col0);
+          tmem_ld_wait();
+          if (c + 2 >= n_chunks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          }
+          float* f = reinterpret_cast<float*>(v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(b4 + j);
+            f[4 * j + 0] = tanh_fast(f[4 * j + 0] + b.x);
+            f[4 * j + 1] = tanh_fast(f[4 * j + 1] + b.y);
+            f[4 * j + 2] = tanh_fast(f[4 * j + 2] + b.z);
+            f[4 * j + 3] = tanh_fast(f[4 * j + 3] + b.w);
+          }
+          if (col0 >= p.n_valid) continue;  // padding columns (warp-uniform)
+          if (want_cos) {
+            // tail pieces: coalesced loads -> staging tile (row r at r * 256 B, 16-byte piece t at t ^ (r & 7)) -> one row per lane
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = i * 2 + (lane >> 4), t = lane & 15;
+              *reinterpret_cast<float4*>(st + r * 256 + ((t ^ (r & 7)) << 4)) = tv[i];
+            }
+            __syncwarp();
+            float cs_dot = 0.f, cs_pp = 0.f, cs_tt = 0.f;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const float4 x = *reinterpret_cast<const float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4));
+              if (col0 + t * 4 < p.n_valid) {
+                cs_dot += f[4 * t] * x.x + f[4 * t + 1] * x.y + f[4 * t + 2] * x.z + f[4 * t + 3] * x.w;
+                cs_pp += f[4 * t] * f[4 * t] + f[4 * t + 1] * f[4 * t + 1] + f[4 * t + 2] * f[4 * t + 2] + f[4 * t + 3] * f[4 * t + 3];
+                cs_tt += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+              }
+            }
+            __syncwarp();
+            float* mine = part + (col0 >> 6) * 3 * kP2Rows;  // one partial triple per 64-column chunk
+            mine[row_in_blk] = cs_dot;
+            mine[kP2Rows + row_in_blk] = cs_pp;
+            mine[2 * kP2Rows + row_in_blk] = cs_tt;
+          }
+          if (want_out) {
+            const long long grow0 = static_cast<long long>(rb) * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
+            if (p.out_f32) {
+#pragma unroll
+              for (int t = 0; t < 16; ++t)
+                *reinterpret_cast<float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4)) =
+                    make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
+              __syncwarp();
+              float* obase = static_cast<float*>(p.gen_out) + col0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int r = i * 2 + (lane >> 4), t = lane & 15;
+                const float4 x = *reinterpret_cast<const float4*>(st + r * 256 + ((t ^ (r & 7)) << 4));
+                const long long gr = grow0 + r;
+                if (gr < p.M && col0 + t * 4 < p.n_valid) *reinterpret_cast<float4*>(obase + gr * p.ld_gen + t * 4) = x;
+              }
+            } else {
+              // bf16: 64 columns = 128 B per row, 8 x 16-byte pieces, swizzled by row & 7
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                uint4 w;
+                w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
+                w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
+                w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
+                w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
+                *reinterpret_cast<uint4*>(st + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
+              }
+              __syncwarp();
+              __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.gen_out) + col0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + (lane >> 3), t = lane & 7;
+                const uint4 w = *reinterpret_cast<const uint4*>(st + r * 128 + ((t ^ (r & 7)) << 4));
+                const long long gr = grow0 + r;
+                if (gr < p.M && col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(obase + gr * p.ld_gen + t * 8) = w;
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (half >= n_chunks) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+        }
+        if (want_cos) {
+          const int old = warp_publish_fetch(p.fin + FIN_G * p.rb_cap + rb, lane);
+          if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
+            fence_acq_rel_gpu();
+            __syncwarp();
+            for (int r = lane; r < kP2Rows; r += 32) {
+              const long long gr = static_cast<long long>(rb) * kP2Rows + r;
+              float d = 0.f, pp = 0.f, tt = 0.f;
+              for (int k = 0; k < p.slots_g; ++k) {
+                d += __ldcg(part + (k * 3 + 0) * kP2Rows + r);
+                pp += __ldcg(part + (k * 3 + 1) * kP2Rows + r);
+                tt += __ldcg(part + (k * 3 + 2) * kP2Rows + r);
+              }
+              // F.cosine_similarity(pred, t, dim=1), eps = 1e-8 on each norm (pro_b_gan_infer.py:202)
+              if (gr < p.M) p.cosine[gr] = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+            }
+          }
+        }
+      }
+      if (tr && lane == 0) busy += clock64() - t_busy0;
+      if (ti) ti[3] = clock64();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait<0>();  // nothing of this warp's staging may be in flight when the CTA exits
+    if (tr && threadIdx.x == 64) { tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy; tr[240] = ph_ld; tr[241] = ph_math; tr[243] = ph_n; }
+  }
+
+  // teardown: neither CTA may exit while the other can still touch its shared memory / barriers / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+  // the last CTA to finish re-arms the scheduler and zeroes the arrival counters for the next launch
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int old = atomicAdd(&p.sched->done, 1);
+    *last_flag = (old == static_cast<int>(gridDim.x) - 1);
+  }
+  __syncthreads();
+  if (*last_flag) {
+    for (int k = 0; k < DEP_KINDS; ++k)
+      for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.ready[k * p.rb_cap + i] = 0;
+    for (int k = 0; k < FIN_KINDS; ++k)
+      for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.fin[k * p.rb_cap + i] = 0;
+    for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) p.queue[i] = 0ull;
+    if (threadIdx.x == 0) { p.sched->q_head = 0; p.sched->q_tail = 0; p.sched->p0_next = 0; p.sched->init = 0; p.sched->done = 0; }
+    if (tr && threadIdx.x == 0) tr[13] = clock64();
+  }
+}
+
+}  // namespace pbg

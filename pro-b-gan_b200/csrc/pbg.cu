@@ -27,6 +27,7 @@
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
 #include "pass_kernel.cuh"
+#include "pass2_kernel.cuh"
 
 using namespace pbg;
 
@@ -47,7 +48,8 @@ struct Linear {
   __nv_bfloat16* w_bf16 = nullptr;
   float* b_pad = nullptr;
   CUtensorMap tmap_w;     // box 64 x block_n
-  CUtensorMap tmap_w128;  // box 64 x 128 (finer tiles for small batches)
+  CUtensorMap tmap_w128;  // box 64 x 128 (finer tiles for small batches; one CTA's half of a 256-wide pair tile)
+  CUtensorMap tmap_w64;   // box 64 x 64  (one CTA's half of a 128-wide pair tile)
 };
 
 struct Workspace {
@@ -189,6 +191,7 @@ int upload_linear(pbg_ctx* c, Linear& l, int n, int k, int kp, const float* w_ho
   PBG_CUDA(c, cudaGetLastError());
   PBG_CUDA(c, cudaStreamSynchronize(c->own_stream));
   PBG_TRY(make_tmap(c, &l.tmap_w128, l.w_bf16, l.np, l.kp, 128));
+  PBG_TRY(make_tmap(c, &l.tmap_w64, l.w_bf16, l.np, l.kp, 64));
   return make_tmap(c, &l.tmap_w, l.w_bf16, l.np, l.kp, l.block_n);
 }
 
@@ -331,6 +334,8 @@ int build_items(pbg_ctx* c, long long rows, bool run_g, bool run_d, ItemList** o
 struct Pass;
 int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
                 void* gen_out, float* scores);
+int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
+                 void* gen_out, float* scores);
 
 struct Pass {
   const float* node_emb = nullptr; long long N = 0;
@@ -372,7 +377,9 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
 
   if (bf) {
-    return launch_pass(c, w, a, gp, off, rows, gen_out, scores);
+    static const bool use_v1 = [] { const char* e = getenv("PBG_PASS_V1"); return e && atoi(e) != 0; }();
+    return use_v1 ? launch_pass(c, w, a, gp, off, rows, gen_out, scores)
+                  : launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
   } else {
     float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
     const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
@@ -457,6 +464,71 @@ int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp,
   const int grid = pass_grid(c);  // phase 0 and the item order assume this many co-resident CTAs
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
     pbg_pass_kernel<<<grid, kPassThreads, PassSmem::kTotal, a.stream>>>(p); }
+  PBG_CUDA(c, cudaGetLastError());
+  return PBG_OK;
+}
+
+// The pair kernel (pass2_kernel.cuh): 256-row blocks, tiles of 256 x {256 | 128}, one CTA pair per tile.
+int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
+                 void* gen_out, float* scores) {
+  static bool attr_set = false;
+  static int attr_dev = -1;
+  if (!attr_set || attr_dev != c->dims.device) {
+    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
+    attr_set = true; attr_dev = c->dims.device;
+  }
+  const int grid = pass_grid(c) & ~1;  // whole pairs
+  Pass2Params p;
+  memset(&p, 0, sizeof p);
+  const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
+  const CUtensorMap* amap[5] = {&w.tm_xg0, &w.tm_xd0, &w.tm_bufA_g, &w.tm_bufD_d, &w.tm_bufB_g};
+  const CUtensorMap* omap[5] = {&w.tmo_bufA, &w.tmo_bufD, &w.tmo_bufB, nullptr, nullptr};
+  const bool on[5] = {a.run_g, a.run_d, a.run_g, a.run_d, a.run_g};
+  static const int pred_of[5] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1};
+  static const int out_of[5] = {DEP_G0, DEP_D0, DEP_G1, -1, -1};
+  static const int epi_of[5] = {PEPI_STORE, PEPI_STORE, PEPI_STORE, PEPI_ROWDOT, PEPI_TANH};
+  const int nrb = static_cast<int>((rows + kP2Rows - 1) / kP2Rows);
+  long long total = 0;
+  for (int k = 0; k < 5; ++k) {
+    if (!on[k]) continue;
+    const Linear& l = *lin[k];
+    const int bn = (l.np % 256 == 0) ? 256 : 128;
+    if (l.np / bn > 255) return fail(c, PBG_ERR_UNSUPPORTED, "layer too wide for the tile index");
+    p.tm_a[k] = *amap[k];
+    p.tm_w[k] = bn == 256 ? l.tmap_w128 : l.tmap_w64;
+    if (omap[k]) p.tm_o[k] = *omap[k];
+    p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], l.b_pad};
+    p.layer_mask |= 1u << k;
+    total += static_cast<long long>(nrb) * (l.np / bn);
+  }
+  if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
+  if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
+  // phase 0: the first row blocks are gathered by the epilogue warps of all CTAs before the roles start (one 4-row
+  // group per warp); the rest of the batch goes through gather items (64 rows each)
+  p.p0_blocks = std::min(nrb, std::max(1, grid * kEpiWarps / kP2GroupsPerBlock));
+  p.phase0_groups = p.p0_blocks * kP2GroupsPerBlock;
+  total += static_cast<long long>(nrb - p.p0_blocks) * kP2GatherPerBlock;
+  p.n_total = static_cast<int>(total);
+  if (total > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
+  p.gather = gp;
+  static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
+  p.poll_ns = poll_env;
+  p.gather_ahead = 16;
+  p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
+  p.queue = w.queue; p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
+  p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
+  if (scores) {
+    p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
+    p.tail_idx = a.tails + off * a.ts; p.tail_stride = a.ts;
+  }
+  p.part_g = w.part_g; p.slots_g = on[IT_G_L2] ? (c->dims.embed_dim + 63) / 64 : 0;  // only the valid columns
+  p.w3 = c->d_w3_pad; p.b3 = c->d_b3;
+  p.logits = a.logits ? a.logits + off : nullptr;
+  p.probs = a.probs ? a.probs + off : nullptr;
+  p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
+  p.trace = c->trace;
+  { LaunchScope ls(c, PBG_K_PASS, a.stream);
+    pbg_pass2_kernel<<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p); }
   PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
