@@ -11,10 +11,17 @@
 // 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).
 //
 //   leader CTA (cluster rank 0)                               peer CTA (rank 1)
-//   warp 0   scheduler: pops tickets, publishes items to      warp 0   TMA producer for its halves of A and W,
-//            both CTAs' rings; TMA producer for its halves             signalling the leader's full barriers
-//   warp 1   MMA issuer (one thread) for the pair             warp 1   idle
+//   warp 0   TMA producer for its halves of A and W           warp 0   TMA producer for its halves of A and W,
+//                                                                      signalling the leader's full barriers
+//   warp 1   MMA issuer (one thread) for the pair             warp 1   scheduler (one thread): pops tickets up to a
+//                                                                      ring's depth ahead, publishes the items to both
+//                                                                      CTAs' rings
 //   warps 2..9  epilogue of its 128 rows / gather items       warps 2..9  epilogue of its 128 rows / gather items
+//
+// Tickets below n_static index a static, topologically ordered item list described by a few segments (small
+// batches: every item; the producers poll the item's dependency counter, after prefetching its W tiles, instead of
+// being pushed); tickets above it index the ready queue (large batches: an item is pushed when its inputs are
+// complete).  Either way a pair works through its tickets in order, which makes any topological order deadlock-free.
 //
 // Epilogues: bias + LeakyReLU -> bf16 -> swizzled staging (double-buffered per warp) -> TMA store; the final
 // discriminator dot and the cosine against the tail embedding are written as per-64-column partials that the last
@@ -42,8 +49,12 @@ struct P2Layer {
   int epi;           // PEPI_*
   int dep_kind;      // DEP_* counter that gates this layer's A operand
   int out_kind;      // DEP_* counter this layer's stores bump, or -1
+  int ldo;           // PEPI_STORE: leading dimension of out (elements)
   const float* bias; // [n_tiles * block_n] fp32, zero padded
+  __nv_bfloat16* out;// PEPI_STORE: next layer's A operand
 };
+
+struct P2Segment { int kind, n_tiles, start, count; };  // static tickets [start, start + count): (kind, n = i % n_tiles, rb = i / n_tiles)
 
 struct alignas(64) Pass2Params {
   CUtensorMap tm_a[5];  // A operand of layer i: xg0, xd0, actG0, actD0, actG1   (box 64 x 128 rows, SWIZZLE_128B)
@@ -56,7 +67,11 @@ struct alignas(64) Pass2Params {
   int phase0_groups;    // 4-row gather groups done by the epilogue warps of all CTAs before the roles start
   int p0_blocks;        // = phase0_groups / 64
   int gather_ahead;     // gather items run this many row blocks ahead of the first-layer tiles
-  int n_total;          // items this launch pushes (and pops) in total
+  int n_total;          // items this launch pops in total (static + pushed)
+  int n_static;         // tickets served from the segment table; pushes are disabled when n_static == n_total
+  int n_seg;
+  P2Segment seg[8];
+  int store_mode;       // PEPI_STORE: 0 = TMA store from the staging tile, 1 = staged transposes + coalesced st.global
   int nrb;              // 256-row blocks in this pass
   int rb_cap;           // stride of the counter arrays
   int M;                // rows in this pass
@@ -84,7 +99,9 @@ struct P2Smem {
   static constexpr int kStagingOff = kP2Stages * kStage;
   static constexpr int kStagingPerWarp = 8192;   // two 4 KB store tiles / one 32 x 64 fp32 transpose tile
   static constexpr int kBarOff = kStagingOff + kEpiWarps * kStagingPerWarp;
-  static constexpr int kTotal = kBarOff + 512 + 1024 /*alignment slack*/;
+  static constexpr int kXchgOff = kBarOff + 256;          // cosine partials handed between the two warps of a quarter
+  static constexpr int kXchgBytes = 4 * 32 * 3 * 4;
+  static constexpr int kTotal = kXchgOff + kXchgBytes + 256 + 1024 /*alignment slack*/;
 };
 static_assert(P2Smem::kTotal <= 232448, "pass2: shared memory budget");
 
@@ -119,36 +136,79 @@ __device__ __forceinline__ int p2_dep_target(const Pass2Params& p, int dep_kind)
 }
 __device__ __forceinline__ void p2_push_gather(const Pass2Params& p, int rb) {
   const int base = atomicAdd(&p.sched->q_tail, kP2GatherPerBlock);
-  for (int u = 0; u < kP2GatherPerBlock; ++u) st_release_gpu_u64(p.queue + base + u, pass_item(IT_GATHER, u, rb));
+  for (int u = 0; u < kP2GatherPerBlock; ++u) st_relaxed_gpu_u64(p.queue + base + u, pass_item(IT_GATHER, u, rb));
 }
-// One thread, after its arrival completed block rb of buffer dep_kind: push the block's consumers.
+// One thread, after its arrival completed block rb of buffer dep_kind: push the block's consumers.  One fence orders
+// everything the producers wrote (acquired through the counter) before the relaxed queue stores that follow it.
 __device__ __forceinline__ void p2_group_done(const Pass2Params& p, int dep_kind, int rb) {
   fence_acq_rel_gpu();
   if (dep_kind == DEP_X) {
     const int ng = (p.layer_mask & (1u << IT_G_L0)) ? p.layer[IT_G_L0].n_tiles : 0;
     const int nd = (p.layer_mask & (1u << IT_D_L0)) ? p.layer[IT_D_L0].n_tiles : 0;
     const int base = atomicAdd(&p.sched->q_tail, ng + nd);
-    for (int n = 0; n < ng; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(IT_G_L0, n, rb));
-    for (int n = 0; n < nd; ++n) st_release_gpu_u64(p.queue + base + ng + n, pass_item(IT_D_L0, n, rb));
+    for (int n = 0; n < ng; ++n) st_relaxed_gpu_u64(p.queue + base + n, pass_item(IT_G_L0, n, rb));
+    for (int n = 0; n < nd; ++n) st_relaxed_gpu_u64(p.queue + base + ng + n, pass_item(IT_D_L0, n, rb));
     if (rb >= p.p0_blocks && rb + p.gather_ahead < p.nrb) p2_push_gather(p, rb + p.gather_ahead);
   } else {
     const int kind = dep_kind == DEP_G0 ? IT_G_L1 : (dep_kind == DEP_D0 ? IT_D_L1 : IT_G_L2);
     const int nt = p.layer[kind].n_tiles;
     const int base = atomicAdd(&p.sched->q_tail, nt);
-    for (int n = 0; n < nt; ++n) st_release_gpu_u64(p.queue + base + n, pass_item(kind, n, rb));
+    for (int n = 0; n < nt; ++n) st_relaxed_gpu_u64(p.queue + base + n, pass_item(kind, n, rb));
   }
 }
 __device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, int rb, int lane, bool async_stores) {
   __syncwarp();
   if (lane == 0) {
     if (async_stores) { tma_store_wait<0>(); fence_proxy_async_all(); }
-    const int old = atom_release_gpu_add(p.ready + dep_kind * p.rb_cap + rb, 1);
-    if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+    int* ctr = p.ready + dep_kind * p.rb_cap + rb;
+    if (p.n_static == p.n_total) {
+      red_release_gpu_add(ctr, 1);  // consumers poll: nobody needs to know who was last
+    } else {
+      const int old = atom_release_gpu_add(ctr, 1);
+      if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+    }
   }
+}
+// A producer thread waits until block rb of buffer dep_kind is complete (static items only).  The data is read by
+// TMA only (async proxy, from L2): the proxy fence orders the counter read before the bulk loads that follow.
+__device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, int rb) {
+  const int target = p2_dep_target(p, dep_kind);
+  const int* ctr = p.ready + dep_kind * p.rb_cap + rb;
+  uint32_t spins = 0;
+  while (ld_relaxed_gpu(ctr) < target) {
+    __nanosleep(p.poll_ns);
+    if (++spins > 4000000u) { printf("pbg: dependency wait timed out (block %d dep %d rb %d)\n", blockIdx.x, dep_kind, rb); __trap(); }
+  }
+  fence_proxy_async_all();
+}
+
+// Tail-embedding pieces of one 64-column chunk for this warp's 32 rows: coalesced 16-byte loads (two rows per
+// instruction) into the warp's staging tile, row r at r * 256 B, piece t at t ^ (r & 7).
+__device__ __forceinline__ void p2_stage_tail(uint8_t* st, unsigned long long trow_bits, int col0, int n_valid, int lane) {
+  float4 tv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = i * 2 + (lane >> 4), t = lane & 15;
+    const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
+    tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tp2 != nullptr && col0 + t * 4 < n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = i * 2 + (lane >> 4), t = lane & 15;
+    *reinterpret_cast<float4*>(st + r * 256 + ((t ^ (r & 7)) << 4)) = tv[i];
+  }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+constexpr uint32_t kItemPoll = 1u << 16;   // ring item flag: the producers poll the dependency counter themselves
+
+// Always 0 (an item's bits 24..31 are never set), but only known at run time: added to the address of a consumer's
+// sched_empty arrive so that the arrive cannot be issued before the load of the ring slot has returned.
+__device__ __forceinline__ uint32_t ring_dep(uint2 it) { return (it.x >> 24) << 3; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPassThreads, 1)
 pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   using L = P2Smem;
   extern __shared__ uint8_t smem_raw[];
@@ -162,11 +222,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   uint2* ring = reinterpret_cast<uint2*>(sched_empty + kP2Ring);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + kP2Ring);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  constexpr int kRingConsumers = 2 * (1 + kEpiWarps) + 1;  // both producers, the MMA issuer, 16 epilogue warps
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 5; ++i) {
@@ -185,8 +247,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       mbar_init(&tmem_empty[s], kP2WarpsPerPair);   // leader's: the epilogue warps of both CTAs
     }
     for (int s = 0; s < kP2Ring; ++s) {
-      mbar_init(&sched_full[s], 1);                       // the leader's scheduler (local + remote arrive)
-      mbar_init(&sched_empty[s], 2 * (1 + kEpiWarps));    // leader's: {MMA | peer producer} + 8 epilogue warps, per CTA
+      mbar_init(&sched_full[s], 1);                 // the scheduler (local + remote arrive)
+      mbar_init(&sched_empty[s], kRingConsumers);   // peer's (the scheduler's CTA)
     }
     fence_mbar_init();
   }
@@ -199,12 +261,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   long long* tr = p.trace ? p.trace + kTraceSlots * blockIdx.x : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); }
 
-  // addresses of the leader's barriers as seen from either CTA
-  const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);
-  const uint32_t lead_sched_empty = mapa_u32(smem_u32(sched_empty), 0);
+  const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);    // the leader's, as seen from either CTA
+  const uint32_t sched_empty_addr = mapa_u32(smem_u32(sched_empty), 1);  // the scheduler CTA's
+  const uint32_t ring_addr = mapa_u32(smem_u32(ring), 1);
+  const bool pushing = p.n_static != p.n_total;
 
   // ---- queue seeding: gather items of the first row blocks past phase 0
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (pushing && blockIdx.x == 0 && threadIdx.x == 0) {
     for (int rb = p.p0_blocks; rb < min(p.nrb, p.p0_blocks + p.gather_ahead); ++rb) p2_push_gather(p, rb);
   }
   // ---- phase 0: the epilogue warps of all CTAs gather the first row blocks, one 4-row group per warp and round
@@ -219,56 +282,69 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     if (tr && threadIdx.x == 64) tr[5] = clock64();
   }
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ scheduler (leader) + TMA producer (both)
+  if (warp == 1 && !leader) {
+    // ------------------------------------------------------------ scheduler (one thread of the peer CTA)
+    if (lane == 0) {
+      uint32_t slot = 0, sphase = 0;
+      long long w_dep = 0;
+      const uint32_t lead_sched_full = mapa_u32(smem_u32(sched_full), 0);
+      for (;;) {
+        const int ticket = atomicAdd(&p.sched->q_head, 1);
+        uint2 it = make_uint2(IT_END, 0u);
+        if (ticket < p.n_static) {
+          int sg = 0;
+          while (sg + 1 < p.n_seg && ticket >= p.seg[sg + 1].start) ++sg;
+          const int i = ticket - p.seg[sg].start;
+          const int nt = p.seg[sg].n_tiles;
+          it = make_uint2(static_cast<uint32_t>(p.seg[sg].kind) | (static_cast<uint32_t>(i % nt) << 8) | kItemPoll,
+                          static_cast<uint32_t>(i / nt));
+        } else if (ticket < p.n_total) {
+          const long long t = tr ? clock64() : 0;
+          unsigned long long d;
+          uint32_t spins = 0;
+          while ((d = ld_relaxed_gpu_u64(p.queue + (ticket - p.n_static))) == 0ull) {
+            __nanosleep(p.poll_ns);
+            if (++spins > 4000000u) { printf("pbg: ready-queue wait timed out (block %d ticket %d of %d)\n", blockIdx.x, ticket, p.n_total); __trap(); }
+          }
+          if (tr) w_dep += clock64() - t;
+          it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
+        }
+        // Ring protocol: the item lives in this (the scheduler's) CTA only; the leader's consumers fetch it with a
+        // remote load after their own sched_full barrier fires.  All arrives use CTA-scope release (a cluster-scope
+        // release is a MEMBAR.ALL.GPU in front of every arrive): the slot is written to local shared memory before
+        // the remote arrive leaves this SM, and a consumer's arrive on sched_empty carries a data dependency on its
+        // load of the slot.
+        mbar_wait(&sched_empty[slot], sphase ^ 1);
+        ring[slot] = it;
+        mbar_arrive(&sched_full[slot]);
+        mbar_arrive_cluster(lead_sched_full + slot * 8);  // release at cluster scope: the slot is visible to the remote loads
+        const uint32_t used = slot, used_phase = sphase;
+        if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+        if ((it.x & 0xff) == IT_END) break;
+        // a gather item keeps the pair's epilogue warps busy without any loads: wait until everybody has picked it up
+        // before popping another ticket, so that an idle scheduler cannot hoard gather items
+        if ((it.x & 0xff) == IT_GATHER) mbar_wait(&sched_empty[used], used_phase);
+      }
+      if (tr) tr[11] = w_dep;
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
       long long w_dep = 0, w_empty = 0, n_items = 0;
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
-      const uint32_t peer_ring = mapa_u32(smem_u32(ring), 1);
-      const uint32_t peer_sched_full = mapa_u32(smem_u32(sched_full), 1);
       for (;;) {
-        uint2 it;
-        if (leader) {
-          const int ticket = atomicAdd(&p.sched->q_head, 1);
-          it = make_uint2(IT_END, 0u);
-          if (ticket < p.n_total) {
-            const long long t = tr ? clock64() : 0;
-            unsigned long long d;
-            uint32_t spins = 0;
-            while ((d = ld_relaxed_gpu_u64(p.queue + ticket)) == 0ull) {
-              __nanosleep(p.poll_ns);
-              if (++spins > 4000000u) { printf("pbg: ready-queue wait timed out (block %d ticket %d of %d)\n", blockIdx.x, ticket, p.n_total); __trap(); }
-            }
-            if (tr) w_dep += clock64() - t;
-            it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
-          }
-          mbar_wait_cluster(&sched_empty[slot], sphase ^ 1);
-          ring[slot] = it;
-          st_cluster_u32x2(peer_ring + slot * 8, it);
-          mbar_arrive(&sched_full[slot]);
-          mbar_arrive_cluster(peer_sched_full + slot * 8);
-        } else {
-          mbar_wait_cluster(&sched_full[slot], sphase);
-          it = ring[slot];
-          mbar_arrive_cluster(lead_sched_empty + slot * 8);
-        }
-        // the item's inputs were complete before it was pushed; they are read by TMA only (async proxy, from L2)
-        fence_proxy_async_all();
-        const uint32_t used = slot;
-        const uint32_t used_phase = sphase;
+        mbar_wait(&sched_full[slot], sphase);
+        const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
+        mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
         const int kind = it.x & 0xff;
         if (kind == IT_END) break;
         long long* ti = (tr && n_items < kTraceItems) ? tr + 16 + 4 * n_items : nullptr;
         if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; ti[1] = 0; }
         ++n_items;
-        if (kind == IT_GATHER) {
-          // no loads to issue: wait until everybody has picked the item up before popping another ticket, so that
-          // an idle scheduler cannot hoard gather items while other pairs have none
-          if (leader) mbar_wait_cluster(&sched_empty[used], used_phase);
-          continue;
-        }
+        if (kind == IT_GATHER) continue;
         const int n_blk = (it.x >> 8) & 0xff;
         const int rb = static_cast<int>(it.y);
         const P2Layer& ly = p.layer[kind];
@@ -276,37 +352,62 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const uint32_t bytes_pair = 2u * (L::kA + static_cast<uint32_t>(w_rows) * kBlockK * 2);
         const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
         const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
-        for (int kb = 0; kb < ly.num_kb; ++kb) {
+        int kb0 = 0;
+        if (it.x & kItemPoll) {
+          // static item: its W tiles do not depend on anything -- put the first ring's worth in flight, then wait
+          // for the A operand's row block, then issue the matching A loads
+          const int npre = min(ly.num_kb, kP2Stages);
+          uint32_t st2 = stage, ph2 = phase;
+          for (int kb = 0; kb < npre; ++kb) {
+            if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[st2], ph2 ^ 1); w_empty += clock64() - t; }
+            else mbar_wait(&empty_bar[st2], ph2 ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[st2], bytes_pair);
+            tma_load_2d_pair(smem + st2 * L::kStage + L::kA, &p.tm_w[kind], lead_full + st2 * 8, kb * kBlockK, w_row);
+            if (++st2 == kP2Stages) { st2 = 0; ph2 ^= 1; }
+          }
+          { const long long t = tr ? clock64() : 0;
+            p2_poll_dep(p, ly.dep_kind, rb);
+            if (tr) { w_dep += clock64() - t; if (ti) ti[1] = clock64(); } }
+          for (int kb = 0; kb < npre; ++kb) {
+            tma_load_2d_pair(smem + stage * L::kStage, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
+            if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
+          }
+          kb0 = npre;
+        } else {
+          // pushed item: its inputs were complete before it was pushed; they are read by TMA only (async proxy)
+          fence_proxy_async_all();
+        }
+        for (int kb = kb0; kb < ly.num_kb; ++kb) {
           if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStage;
-          uint8_t* sb = sa + L::kA;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
-          tma_load_2d_pair(sb, &p.tm_w[kind], lead_full + stage * 8, kb * kBlockK, w_row);
+          tma_load_2d_pair(sa + L::kA, &p.tm_w[kind], lead_full + stage * 8, kb * kBlockK, w_row);
           tma_load_2d_pair(sa, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
           if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
         }
       }
-      if (tr) { tr[1] = w_empty; tr[2] = clock64(); tr[11] = w_dep; tr[12] = n_items; }
+      if (tr) { tr[1] = w_empty; tr[2] = clock64(); tr[12] = n_items; if (leader) tr[11] = w_dep; }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
-      long long w_full = 0, w_tmem = 0, n_kb = 0;
+      long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0;
       for (;;) {
-        mbar_wait(&sched_full[slot], sphase);
-        const uint2 it = ring[slot];
-        mbar_arrive(&sched_empty[slot]);
+        if (tr) { const long long t = clock64(); mbar_wait(&sched_full[slot], sphase); w_item += clock64() - t; }
+        else mbar_wait(&sched_full[slot], sphase);
+        const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
+        mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
         const int kind = it.x & 0xff;
         if (kind == IT_END) break;
         if (kind == IT_GATHER) continue;
         const P2Layer& ly = p.layer[kind];
         const uint32_t idesc = make_idesc_bf16(kP2Rows, static_cast<uint32_t>(ly.block_n));
-        if (tr) { const long long t = clock64(); mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
-        else mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        if (tr) { const long long t = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
+        else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < ly.num_kb; ++kb) {
@@ -324,7 +425,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         umma_commit_pair(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; }
+      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; tr[15] = w_item; }
     }
     __syncwarp();
   } else {
@@ -334,24 +435,32 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     const int half = wep >> 2;         // which half of a tile's 64-column chunks this warp takes
     uint8_t* st = smem + L::kStagingOff + wep * L::kStagingPerWarp;
     uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0, buf = 0;
-    long long w_acc = 0, busy = 0, ph_ld = 0, ph_math = 0, ph_n = 0;
+    long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0;
     int item_no = 0;
     int pend_kind = -1, pend_rb = 0;   // previous tile's block: announced once its bulk stores have completed
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
-    for (;;) {
+    // Deferred arrival: a tile's activation stores are announced (bulk-store completion wait + release increment of
+    // the block's counter) where this warp would otherwise idle -- while its next TMEM load is in flight, or before
+    // it blocks on the ring / an accumulator that is not ready yet.  It is never postponed past a point where the
+    // warp can block indefinitely: the item it would wait for may depend on exactly this arrival.
+    auto flush_pend = [&]() {
       if (pend_kind >= 0) { p2_arrive(p, pend_kind, pend_rb, lane, true); pend_kind = -1; }
-      if (leader) mbar_wait(&sched_full[slot], sphase); else mbar_wait_cluster(&sched_full[slot], sphase);
-      const uint2 it = ring[slot];
+    };
+    for (;;) {
+      if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) flush_pend();
+      mbar_wait(&sched_full[slot], sphase);
+      const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_sched_empty + slot * 8);
+      if (lane == 0) mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
       if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
       const int kind = it.x & 0xff;
-      if (kind == IT_END) break;
+      if (kind == IT_END) { flush_pend(); break; }
       const int n_blk = (it.x >> 8) & 0xff;
       const int rb = static_cast<int>(it.y);
       long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
       ++item_no;
       if (kind == IT_GATHER) {
+        flush_pend();
         if (ti) ti[2] = clock64();
         pass_gather_group(p.gather, static_cast<long long>(rb) * kP2GroupsPerBlock + n_blk * kP2WarpsPerPair + rank * kEpiWarps + wep, lane);
         p2_arrive(p, DEP_X, rb, lane, false);
@@ -365,10 +474,15 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       const int n_chunks = ly.block_n >> 6;   // 64-column chunks per tile; this warp takes c = half, half + 2, ...
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
 
-      // PEPI_TANH prefetch (before the accumulator wait): tail index and the tail row pieces of the first chunk
+      // PEPI_TANH prefetch (before the accumulator wait, i.e. behind the tile's MMA time): tail index, then the tail
+      // row pieces of this warp's first chunk, coalesced, into the staging tile
       const bool want_cos = ly.epi == PEPI_TANH && p.cosine != nullptr;
       unsigned long long trow_bits = 0ull;
-      float4 tv[16];
+      if (ly.epi == PEPI_TANH) {
+        // the staging tile may still be the source of an activation store issued by an earlier tile of this warp
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
       if (want_cos) {
         const float* trow = nullptr;
         if (row_ok) {
@@ -377,19 +491,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           trow = p.tail_tab + tid * p.n_valid;
         }
         trow_bits = reinterpret_cast<unsigned long long>(trow);
-        if (half < n_chunks) {
-          const int col0 = n0 + half * 64;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = i * 2 + (lane >> 4), t = lane & 15;
-            const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
-            tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tp2 != nullptr && col0 + t * 4 < p.n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
-          }
-        }
+        if (half < n_chunks) p2_stage_tail(st, trow_bits, n0 + half * 64, p.n_valid, lane);
       }
       {
         const long long t = (tr && lane == 0) ? clock64() : 0;
+        if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&tmem_full[acc], acc_phase))) flush_pend();
         mbar_wait(&tmem_full[acc], acc_phase);
         if (tr && lane == 0) { w_acc += clock64() - t; }
         if (ti) ti[2] = clock64();
@@ -398,58 +504,87 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       tc_fence_after();
 
       if (ly.epi == PEPI_STORE) {
-        // ---- bias + LeakyReLU -> bf16 -> swizzled staging tile -> one TMA store per 32-row x 64-column chunk
+        // ---- bias + LeakyReLU -> bf16 -> swizzled staging tile -> global (TMA store, or transposed st.global)
         const bool tp = tr && threadIdx.x == 64;
-        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
         const float slope = p.slope;
         const float* const bias_tile = ly.bias + n0;
         const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
+        // 32-column TMEM loads, software pipelined: the next load is in flight while the previous one is converted
+        uint32_t va[32], vb[32];
+        flush_pend();  // the previous tile's stores have had a whole accumulator wait to complete
+        if (half < n_chunks) tmem_ld_32x32_ptr(taddr + half * 64, va);
         for (int c = half; c < n_chunks; c += 2) {
           if (tp) tq0 = clock64();
           const float4* b4 = reinterpret_cast<const float4*>(bias_tile + c * 64);
-          uint32_t v[64];
-          tmem_ld_32x32_ptr(taddr + c * 64, v);
-          tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
           // this staging buffer is free once the bulk store issued two chunks ago has read it
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
+          if (p.store_mode == 0) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+          if (tp) tq1 = clock64();
           uint8_t* sbuf = st + buf * 4096;
           tmem_ld_wait();
-          if (c + 2 >= n_chunks) {  // this warp's last read of the accumulator stage
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
-          }
-          if (tp) tq1 = clock64();
+          tmem_ld_32x32_ptr(taddr + c * 64 + 32, vb);
+          if (tp) tq2 = clock64();
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
+          for (int t = 0; t < 4; ++t) {
             const float4 ba = __ldg(b4 + 2 * t), bb = __ldg(b4 + 2 * t + 1);
             uint4 w;
-            w.x = bias_leaky_pack(v[8 * t + 0], v[8 * t + 1], ba.x, ba.y, slope);
-            w.y = bias_leaky_pack(v[8 * t + 2], v[8 * t + 3], ba.z, ba.w, slope);
-            w.z = bias_leaky_pack(v[8 * t + 4], v[8 * t + 5], bb.x, bb.y, slope);
-            w.w = bias_leaky_pack(v[8 * t + 6], v[8 * t + 7], bb.z, bb.w, slope);
+            w.x = bias_leaky_pack(va[8 * t + 0], va[8 * t + 1], ba.x, ba.y, slope);
+            w.y = bias_leaky_pack(va[8 * t + 2], va[8 * t + 3], ba.z, ba.w, slope);
+            w.z = bias_leaky_pack(va[8 * t + 4], va[8 * t + 5], bb.x, bb.y, slope);
+            w.w = bias_leaky_pack(va[8 * t + 6], va[8 * t + 7], bb.z, bb.w, slope);
             *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
           }
-          fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
-            tma_store_commit();
+          tmem_ld_wait();
+          if (c + 2 < n_chunks) {
+            tmem_ld_32x32_ptr(taddr + (c + 2) * 64, va);
+          } else {  // this warp's last read of the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4 ba = __ldg(b4 + 8 + 2 * t), bb = __ldg(b4 + 8 + 2 * t + 1);
+            uint4 w;
+            w.x = bias_leaky_pack(vb[8 * t + 0], vb[8 * t + 1], ba.x, ba.y, slope);
+            w.y = bias_leaky_pack(vb[8 * t + 2], vb[8 * t + 3], ba.z, ba.w, slope);
+            w.z = bias_leaky_pack(vb[8 * t + 4], vb[8 * t + 5], bb.x, bb.y, slope);
+            w.w = bias_leaky_pack(vb[8 * t + 6], vb[8 * t + 7], bb.z, bb.w, slope);
+            *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((4 + t) ^ (lane & 7)) << 4)) = w;
+          }
+          if (tp) tq3 = clock64();
+          if (p.store_mode == 0) {
+            fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
+              tma_store_commit();
+            }
+          } else {
+            __syncwarp();
+            __nv_bfloat16* obase = ly.out + static_cast<size_t>(row0) * ly.ldo + n0 + c * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3), t = lane & 7;
+              const uint4 w = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((t ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * ly.ldo + t * 8) = w;
+            }
           }
           buf ^= 1;
-          if (tp) { tq2 = clock64(); ph_ld += tq1 - tq0; ph_math += tq2 - tq1; ph_n += 1; }
+          if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; }
         }
         if (half >= n_chunks) {  // narrow tile: this warp had no chunk, still has to release the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
-        pend_kind = ly.out_kind; pend_rb = rb;
+        if (p.store_mode == 0) { pend_kind = ly.out_kind; pend_rb = rb; }
+        else p2_arrive(p, ly.out_kind, rb, lane, false);
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block
         const float slope = p.slope;
+        flush_pend();
         float* part = p.part_d + (static_cast<size_t>(rb) * p.slots_d) * kP2Rows;
         for (int c = half; c < n_chunks; c += 2) {
           uint32_t v[64];
@@ -461,7 +596,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           if (c + 2 >= n_chunks) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+            if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
           }
           float rowdot = 0.f;
 #pragma unroll
@@ -477,18 +612,28 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (half >= n_chunks) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
         const int old = warp_publish_fetch(p.fin + FIN_D * p.rb_cap + rb, lane);
         if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
           fence_acq_rel_gpu();
           __syncwarp();
-          for (int r = lane; r < kP2Rows; r += 32) {
-            const long long gr = static_cast<long long>(rb) * kP2Rows + r;
-            float s = 0.f;
-            for (int k = 0; k < p.slots_d; ++k) s += __ldcg(part + k * kP2Rows + r);
+          // 8 rows per lane; all loads of a row group in flight together, summed in slot order
+          float s[kP2Rows / 32];
+#pragma unroll
+          for (int j = 0; j < kP2Rows / 32; ++j) s[j] = 0.f;
+          for (int k = 0; k < p.slots_d; ++k) {
+            float x[kP2Rows / 32];
+#pragma unroll
+            for (int j = 0; j < kP2Rows / 32; ++j) x[j] = __ldcg(part + k * kP2Rows + j * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < kP2Rows / 32; ++j) s[j] += x[j];
+          }
+#pragma unroll
+          for (int j = 0; j < kP2Rows / 32; ++j) {
+            const long long gr = static_cast<long long>(rb) * kP2Rows + j * 32 + lane;
             if (gr < p.M) {
-              const float logit = s + p.b3;
+              const float logit = s[j] + p.b3;
               p.logits[gr] = logit;
               if (p.probs != nullptr) p.probs[gr] = 1.f / (1.f + __expf(-logit));
             }
@@ -496,31 +641,22 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         }
       } else {
         // ---- PEPI_TANH: bias + tanh -> generator output (fp32 / bf16), optional cosine vs the tail embedding
+        flush_pend();
         const bool want_out = p.gen_out != nullptr;
+        const bool in_cta = ly.n_tiles == 1 && n_chunks == 2;  // the whole output row lives in this quarter's two warps
         float* part = p.part_g + (static_cast<size_t>(rb) * p.slots_g) * 3 * kP2Rows;
-        // the staging tile may still be the source of an activation store issued by an earlier tile of this warp
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
         for (int c = half; c < n_chunks; c += 2) {
           const int col0 = n0 + c * 64;
+          if (want_cos && c != half) p2_stage_tail(st, trow_bits, col0, p.n_valid, lane);  // later chunks of a wide tile
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
-          if (want_cos && c != half) {  // later chunks of a wide tile: fetch their tail pieces now
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int r = i * 2 + (lane >> 4), t = lane & 15;
-              const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
-              tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (tp2 != nullptr && col0 + t * 4 < p.n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
-            }
-          }
           const float4* b4 = reinterpret_cast<const float4*>(ly.bias + col0);
           tmem_ld_wait();
           if (c + 2 >= n_chunks) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+            if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
           }
           float* f = reinterpret_cast<float*>(v);
 #pragma unroll
@@ -531,32 +667,41 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             f[4 * j + 2] = tanh_fast(f[4 * j + 2] + b.z);
             f[4 * j + 3] = tanh_fast(f[4 * j + 3] + b.w);
           }
-          if (col0 >= p.n_valid) continue;  // padding columns (warp-uniform)
           if (want_cos) {
-            // tail pieces: coalesced loads -> staging tile (row r at r * 256 B, 16-byte piece t at t ^ (r & 7)) -> one row per lane
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int r = i * 2 + (lane >> 4), t = lane & 15;
-              *reinterpret_cast<float4*>(st + r * 256 + ((t ^ (r & 7)) << 4)) = tv[i];
-            }
-            __syncwarp();
+            // tail pieces are in the staging tile: one row per lane
             float cs_dot = 0.f, cs_pp = 0.f, cs_tt = 0.f;
+            if (col0 < p.n_valid) {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const float4 x = *reinterpret_cast<const float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4));
-              if (col0 + t * 4 < p.n_valid) {
-                cs_dot += f[4 * t] * x.x + f[4 * t + 1] * x.y + f[4 * t + 2] * x.z + f[4 * t + 3] * x.w;
-                cs_pp += f[4 * t] * f[4 * t] + f[4 * t + 1] * f[4 * t + 1] + f[4 * t + 2] * f[4 * t + 2] + f[4 * t + 3] * f[4 * t + 3];
-                cs_tt += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+              for (int t = 0; t < 16; ++t) {
+                const float4 x = *reinterpret_cast<const float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4));
+                if (col0 + t * 4 < p.n_valid) {
+                  cs_dot += f[4 * t] * x.x + f[4 * t + 1] * x.y + f[4 * t + 2] * x.z + f[4 * t + 3] * x.w;
+                  cs_pp += f[4 * t] * f[4 * t] + f[4 * t + 1] * f[4 * t + 1] + f[4 * t + 2] * f[4 * t + 2] + f[4 * t + 3] * f[4 * t + 3];
+                  cs_tt += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                }
               }
             }
             __syncwarp();
-            float* mine = part + (col0 >> 6) * 3 * kP2Rows;  // one partial triple per 64-column chunk
-            mine[row_in_blk] = cs_dot;
-            mine[kP2Rows + row_in_blk] = cs_pp;
-            mine[2 * kP2Rows + row_in_blk] = cs_tt;
+            if (in_cta) {
+              // the two warps of this lane quarter hold the row's two halves: the upper one hands its sums over
+              // through shared memory, the lower one finishes (fixed order: columns 0..63 + columns 64..127)
+              float* xq = xchg + (q * 32 + lane) * 3;
+              if (half == 1) { xq[0] = cs_dot; xq[1] = cs_pp; xq[2] = cs_tt; }
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              if (half == 0) {
+                const float d = cs_dot + xq[0], pp = cs_pp + xq[1], tt = cs_tt + xq[2];
+                // F.cosine_similarity(pred, t, dim=1), eps = 1e-8 on each norm (pro_b_gan_infer.py:202)
+                if (row_ok) p.cosine[grow] = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+              }
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the slot may be rewritten after this
+            } else if (col0 < p.n_valid) {
+              float* mine = part + (col0 >> 6) * 3 * kP2Rows;  // one partial triple per 64-column chunk
+              mine[row_in_blk] = cs_dot;
+              mine[kP2Rows + row_in_blk] = cs_pp;
+              mine[2 * kP2Rows + row_in_blk] = cs_tt;
+            }
           }
-          if (want_out) {
+          if (want_out && col0 < p.n_valid) {
             const long long grow0 = static_cast<long long>(rb) * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
             if (p.out_f32) {
 #pragma unroll
@@ -599,9 +744,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (half >= n_chunks) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_tmem_empty + acc * 8);
+          if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
-        if (want_cos) {
+        if (want_cos && !in_cta) {
           const int old = warp_publish_fetch(p.fin + FIN_G * p.rb_cap + rb, lane);
           if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
             fence_acq_rel_gpu();
@@ -614,7 +759,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 pp += __ldcg(part + (k * 3 + 1) * kP2Rows + r);
                 tt += __ldcg(part + (k * 3 + 2) * kP2Rows + r);
               }
-              // F.cosine_similarity(pred, t, dim=1), eps = 1e-8 on each norm (pro_b_gan_infer.py:202)
               if (gr < p.M) p.cosine[gr] = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
             }
           }
@@ -625,7 +769,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();  // nothing of this warp's staging may be in flight when the CTA exits
-    if (tr && threadIdx.x == 64) { tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy; tr[240] = ph_ld; tr[241] = ph_math; tr[243] = ph_n; }
+    if (tr && threadIdx.x == 64) {
+      tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
+      tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
+    }
   }
 
   // teardown: neither CTA may exit while the other can still touch its shared memory / barriers / TMEM
@@ -648,7 +795,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.ready[k * p.rb_cap + i] = 0;
     for (int k = 0; k < FIN_KINDS; ++k)
       for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.fin[k * p.rb_cap + i] = 0;
-    for (int i = threadIdx.x; i < p.n_total; i += blockDim.x) p.queue[i] = 0ull;
+    for (int i = threadIdx.x; i < p.n_total - p.n_static; i += blockDim.x) p.queue[i] = 0ull;
     if (threadIdx.x == 0) { p.sched->q_head = 0; p.sched->q_tail = 0; p.sched->p0_next = 0; p.sched->init = 0; p.sched->done = 0; }
     if (tr && threadIdx.x == 0) tr[13] = clock64();
   }

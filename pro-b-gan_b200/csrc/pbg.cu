@@ -488,6 +488,8 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   static const int out_of[5] = {DEP_G0, DEP_D0, DEP_G1, -1, -1};
   static const int epi_of[5] = {PEPI_STORE, PEPI_STORE, PEPI_STORE, PEPI_ROWDOT, PEPI_TANH};
   const int nrb = static_cast<int>((rows + kP2Rows - 1) / kP2Rows);
+  __nv_bfloat16* outs[5] = {(__nv_bfloat16*)w.bufA, (__nv_bfloat16*)w.bufD, (__nv_bfloat16*)w.bufB, nullptr, nullptr};
+  const int ldos[5] = {c->hgp, c->hdp, c->hgp, 0, 0};
   long long total = 0;
   for (int k = 0; k < 5; ++k) {
     if (!on[k]) continue;
@@ -497,7 +499,7 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     p.tm_a[k] = *amap[k];
     p.tm_w[k] = bn == 256 ? l.tmap_w128 : l.tmap_w64;
     if (omap[k]) p.tm_o[k] = *omap[k];
-    p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], l.b_pad};
+    p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], ldos[k], l.b_pad, outs[k]};
     p.layer_mask |= 1u << k;
     total += static_cast<long long>(nrb) * (l.np / bn);
   }
@@ -507,13 +509,35 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   // group per warp); the rest of the batch goes through gather items (64 rows each)
   p.p0_blocks = std::min(nrb, std::max(1, grid * kEpiWarps / kP2GroupsPerBlock));
   p.phase0_groups = p.p0_blocks * kP2GroupsPerBlock;
-  total += static_cast<long long>(nrb - p.p0_blocks) * kP2GatherPerBlock;
+  if (nrb <= p.p0_blocks) {
+    // small batch: every item is a static ticket, layer by layer (a topological order); the producers poll the
+    // dependency counters and nothing is pushed
+    static const char* order_env = getenv("PBG_SEG_ORDER");
+    int order[5] = {IT_G_L0, IT_D_L0, IT_G_L1, IT_D_L1, IT_G_L2};
+    if (order_env && strlen(order_env) == 5)
+      for (int i = 0; i < 5; ++i) order[i] = order_env[i] - '0';
+    int start = 0;
+    for (int i = 0; i < 5; ++i) {
+      const int k = order[i];
+      if (k < 0 || k > 4 || !on[k]) continue;
+      const int cnt = nrb * p.layer[k].n_tiles;
+      p.seg[p.n_seg++] = P2Segment{k, p.layer[k].n_tiles, start, cnt};
+      start += cnt;
+    }
+    p.n_static = start;
+    if (start != total) return fail(c, PBG_ERR_INVALID, "internal: static item list does not cover the pass");
+  } else {
+    total += static_cast<long long>(nrb - p.p0_blocks) * kP2GatherPerBlock;
+  }
   p.n_total = static_cast<int>(total);
-  if (total > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
+  if (total - p.n_static > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
+  static const int store_env = [] { const char* e = getenv("PBG_STORE_MODE"); return e ? atoi(e) : 0; }();
+  p.store_mode = store_env;
   p.gather = gp;
   static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
   p.poll_ns = poll_env;
-  p.gather_ahead = 16;
+  static const int ahead_env = [] { const char* e = getenv("PBG_GATHER_AHEAD"); return e ? atoi(e) : 32; }();
+  p.gather_ahead = ahead_env;
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.queue = w.queue; p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
@@ -529,7 +553,14 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.trace = c->trace;
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
     pbg_pass2_kernel<<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p); }
-  PBG_CUDA(c, cudaGetLastError());
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, pbg_pass2_kernel);
+    return fail(c, PBG_ERR_CUDA, "pass kernel launch failed: %s (grid %d x %d threads, %d regs/thread, %zu B static + %d B dynamic smem, "
+                "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kPassThreads, fa.numRegs,
+                fa.sharedSizeBytes, P2Smem::kTotal, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
+  }
   return PBG_OK;
 }
 

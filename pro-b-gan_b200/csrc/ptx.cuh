@@ -55,6 +55,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// Non-blocking probe of a phase (try_wait may suspend the thread for a system-defined time when the phase is open).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
 #ifndef PBG_HANG_GUARD
 #define PBG_HANG_GUARD 1
 #endif
@@ -66,7 +81,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > 4000000u) {
-      printf("pbg: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      printf("pbg: mbarrier wait timed out (block %d thread %d parity %u barrier @%u)\n", blockIdx.x, threadIdx.x, parity,
+             smem_u32(bar) & 0x3ffu);
       __trap();
     }
   }
@@ -202,6 +218,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
 // arrive on an mbarrier anywhere in the cluster (address from mapa_u32); release at cluster scope
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Arrive on an mbarrier of another CTA of the cluster with the default (release, CTA-scope) semantics: no
+// MEMBAR.ALL.GPU in front of it.  For barriers that order TMEM / ring-slot reuse, not generic global data.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint2 ld_cluster_u32x2(uint32_t cluster_addr) {
+  uint2 v;
+  asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

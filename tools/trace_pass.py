@@ -62,8 +62,9 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     P(f"   epilogue warp 2: acc wait {hdr[:, 7].mean():.0f}  busy {hdr[:, 10].mean():.0f}")
     ph = t[:, 240:246]
     nchunk = ph[:, 3].clamp_min(1); ntile = ph[:, 5].clamp_min(1)
-    P(f"   STORE epilogue phases (warp 2, clk per 64-col chunk): tmem ld+wait {(ph[:, 0] / nchunk).mean():.0f}  bias+math+STS {(ph[:, 1] / nchunk).mean():.0f}"
-      f"  LDS+STG {(ph[:, 2] * 0).mean():.0f};  publish per tile {(ph[:, 4] * 0).mean():.0f}")
+    P(f"   mma: waiting for an item {hdr[:, 15][hdr[:, 9] > 0].mean():.0f}")
+    P(f"   STORE epilogue phases (warp 2, clk per 64-col chunk): staging free {(ph[:, 4] / nchunk).mean():.0f}  tmem ld+wait {(ph[:, 0] / nchunk).mean():.0f}"
+      f"  bias+math+STS {(ph[:, 1] / nchunk).mean():.0f}  store {(ph[:, 2] / nchunk).mean():.0f}")
     kind = raw0 & 0xff
     mblk = (raw0 >> 8) & 0xfff
     valid = raw0 != 0
