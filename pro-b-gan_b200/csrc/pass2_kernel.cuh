@@ -35,7 +35,7 @@
 
 namespace pbg {
 
-constexpr int kP2Stages = 5;
+constexpr int kP2Stages = 4;
 constexpr int kP2Ring = 4;
 constexpr int kP2Rows = 256;                        // rows of one pair tile = one dependency block
 constexpr int kP2GroupsPerBlock = kP2Rows / 4;      // 4-row gather groups per block
@@ -50,6 +50,7 @@ struct P2Layer {
   int dep_kind;      // DEP_* counter that gates this layer's A operand
   int out_kind;      // DEP_* counter this layer's stores bump, or -1
   int ldo;           // PEPI_STORE: leading dimension of out (elements)
+  int bias_off;      // offset (floats) of this layer's bias in the shared-memory copy, or -1: read it from global
   const float* bias; // [n_tiles * block_n] fp32, zero padded
   __nv_bfloat16* out;// PEPI_STORE: next layer's A operand
 };
@@ -87,6 +88,7 @@ struct alignas(64) Pass2Params {
   int slots_g;
   // discriminator output (PEPI_ROWDOT)
   const float* w3; float b3; float* logits; float* probs;
+  int w3_off;           // offset (floats) of w3 in the shared-memory copy, or -1
   float* part_d;        // [nrb][slots_d][256]
   int slots_d;
   long long* trace;
@@ -98,7 +100,9 @@ struct P2Smem {
   static constexpr int kStage = kA + kW;
   static constexpr int kStagingOff = kP2Stages * kStage;
   static constexpr int kStagingPerWarp = 8192;   // two 4 KB store tiles / one 32 x 64 fp32 transpose tile
-  static constexpr int kBarOff = kStagingOff + kEpiWarps * kStagingPerWarp;
+  static constexpr int kBiasOff = kStagingOff + kEpiWarps * kStagingPerWarp;
+  static constexpr int kBiasFloats = 6144;       // every layer's padded bias + the final dot weights, when they fit
+  static constexpr int kBarOff = kBiasOff + kBiasFloats * 4;
   static constexpr int kXchgOff = kBarOff + 256;          // cosine partials handed between the two warps of a quarter
   static constexpr int kXchgBytes = 4 * 32 * 3 * 4;
   static constexpr int kTotal = kXchgOff + kXchgBytes + 256 + 1024 /*alignment slack*/;
@@ -140,7 +144,7 @@ __device__ __forceinline__ void p2_push_gather(const Pass2Params& p, int rb) {
 }
 // One thread, after its arrival completed block rb of buffer dep_kind: push the block's consumers.  One fence orders
 // everything the producers wrote (acquired through the counter) before the relaxed queue stores that follow it.
-__device__ __forceinline__ void p2_group_done(const Pass2Params& p, int dep_kind, int rb) {
+__device__ __noinline__ void p2_group_done(const Pass2Params& p, int dep_kind, int rb) {
   fence_acq_rel_gpu();
   if (dep_kind == DEP_X) {
     const int ng = (p.layer_mask & (1u << IT_G_L0)) ? p.layer[IT_G_L0].n_tiles : 0;
@@ -156,12 +160,26 @@ __device__ __forceinline__ void p2_group_done(const Pass2Params& p, int dep_kind
     for (int n = 0; n < nt; ++n) st_relaxed_gpu_u64(p.queue + base + n, pass_item(kind, n, rb));
   }
 }
-__device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, int rb, int lane, bool async_stores) {
+// A warp announces "my part of block rb of buffer dep_kind is in global memory".
+//   generic stores (gather): the warp barrier orders every lane's stores before lane 0's release increment.
+//   bulk stores (activations): lane 0 issued them; cp.async.bulk.wait_group 0 returns once they have been performed
+//   (in L2, the point of coherence for every consumer, which reads them with TMA after a relaxed poll of the counter
+//   and a proxy fence), so the increment itself is relaxed -- a release here is a MEMBAR.ALL.GPU on the critical path
+//   of every layer-to-layer hand-off.
+__device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, int rb, int lane, bool async_stores,
+                                          long long* t_wait = nullptr) {
   __syncwarp();
   if (lane == 0) {
-    if (async_stores) { tma_store_wait<0>(); fence_proxy_async_all(); }
     int* ctr = p.ready + dep_kind * p.rb_cap + rb;
-    if (p.n_static == p.n_total) {
+    const bool pushing = p.n_static != p.n_total;
+    if (async_stores) {
+      const long long t0 = t_wait ? clock64() : 0;
+      tma_store_wait<0>();
+      if (t_wait) *t_wait += clock64() - t0;
+      if (!pushing) { red_relaxed_gpu_add(ctr, 1); return; }
+      const int old = atom_relaxed_gpu_add(ctr, 1);
+      if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+    } else if (!pushing) {
       red_release_gpu_add(ctr, 1);  // consumers poll: nobody needs to know who was last
     } else {
       const int old = atom_release_gpu_add(ctr, 1);
@@ -177,7 +195,7 @@ __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, 
   uint32_t spins = 0;
   while (ld_relaxed_gpu(ctr) < target) {
     __nanosleep(p.poll_ns);
-    if (++spins > 4000000u) { printf("pbg: dependency wait timed out (block %d dep %d rb %d)\n", blockIdx.x, dep_kind, rb); __trap(); }
+    if (++spins > 4000000u) pbg_wait_timed_out("dependency (kind, row block)", dep_kind, rb);
   }
   fence_proxy_async_all();
 }
@@ -208,6 +226,8 @@ constexpr uint32_t kItemPoll = 1u << 16;   // ring item flag: the producers poll
 // sched_empty arrive so that the arrive cannot be issued before the load of the ring slot has returned.
 __device__ __forceinline__ uint32_t ring_dep(uint2 it) { return (it.x >> 24) << 3; }
 
+// TR: the diagnostics instance (pbg_debug_trace); the production instance carries no trace code or registers.
+template <bool TR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPassThreads, 1)
 pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   using L = P2Smem;
@@ -223,11 +243,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + kP2Ring);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
   float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
+  float* sbias = reinterpret_cast<float*>(smem + L::kBiasOff);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  const long long t_entry = (TR && p.trace && threadIdx.x == 0) ? static_cast<long long>(globaltimer_ns()) : 0;
   constexpr int kRingConsumers = 2 * (1 + kEpiWarps) + 1;  // both producers, the MMA issuer, 16 epilogue warps
 
   if (threadIdx.x == 0) {
@@ -252,14 +274,26 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     }
     fence_mbar_init();
   }
+  // Biases (and the final dot weights) live in shared memory for the whole launch: with ~224 KB of the SM carved out
+  // as shared memory there is next to no L1 left, so a bias read through the global path costs an L2 round trip.
+  for (int k = 0; k < 5; ++k) {
+    if ((p.layer_mask & (1u << k)) && p.layer[k].bias_off >= 0) {
+      const int n = p.layer[k].n_tiles * p.layer[k].block_n;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) sbias[p.layer[k].bias_off + i] = __ldg(p.layer[k].bias + i);
+    }
+  }
+  if ((p.layer_mask & (1u << IT_D_L1)) && p.w3_off >= 0) {
+    const int n = p.layer[IT_D_L1].n_tiles * p.layer[IT_D_L1].block_n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sbias[p.w3_off + i] = __ldg(p.w3 + i);
+  }
   if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  long long* tr = p.trace ? p.trace + kTraceSlots * blockIdx.x : nullptr;
-  if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); }
+  long long* const tr = (TR && p.trace) ? p.trace + kTraceSlots * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); tr[254] = t_entry; }
 
   const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);    // the leader's, as seen from either CTA
   const uint32_t sched_empty_addr = mapa_u32(smem_u32(sched_empty), 1);  // the scheduler CTA's
@@ -276,7 +310,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     const int gw = static_cast<int>(blockIdx.x) * kEpiWarps + (warp - 2);
     const int gstep = static_cast<int>(gridDim.x) * kEpiWarps;
     for (int g = gw; g < p.phase0_groups; g += gstep) {
+      if (tr && threadIdx.x == 64) tr[249] = clock64();
       pass_gather_group(p.gather, g, lane);
+      if (tr && threadIdx.x == 64) tr[250] = clock64();
       p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
     }
     if (tr && threadIdx.x == 64) tr[5] = clock64();
@@ -304,7 +340,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           uint32_t spins = 0;
           while ((d = ld_relaxed_gpu_u64(p.queue + (ticket - p.n_static))) == 0ull) {
             __nanosleep(p.poll_ns);
-            if (++spins > 4000000u) { printf("pbg: ready-queue wait timed out (block %d ticket %d of %d)\n", blockIdx.x, ticket, p.n_total); __trap(); }
+            if (++spins > 4000000u) pbg_wait_timed_out("ready-queue (ticket, total)", ticket, p.n_total);
           }
           if (tr) w_dep += clock64() - t;
           it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
@@ -435,7 +471,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     const int half = wep >> 2;         // which half of a tile's 64-column chunks this warp takes
     uint8_t* st = smem + L::kStagingOff + wep * L::kStagingPerWarp;
     uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0, buf = 0;
-    long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0;
+    long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     int pend_kind = -1, pend_rb = 0;   // previous tile's block: announced once its bulk stores have completed
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
@@ -443,8 +479,14 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     // the block's counter) where this warp would otherwise idle -- while its next TMEM load is in flight, or before
     // it blocks on the ring / an accumulator that is not ready yet.  It is never postponed past a point where the
     // warp can block indefinitely: the item it would wait for may depend on exactly this arrival.
+    long long pf_delay = 0, pf_wait = 0, pf_total = 0, pf_n = 0, t_pend = 0;
     auto flush_pend = [&]() {
-      if (pend_kind >= 0) { p2_arrive(p, pend_kind, pend_rb, lane, true); pend_kind = -1; }
+      if (pend_kind >= 0) {
+        const long long t0 = (tr && threadIdx.x == 64) ? clock64() : 0;
+        p2_arrive(p, pend_kind, pend_rb, lane, true, (tr && threadIdx.x == 64) ? &pf_wait : nullptr);
+        pend_kind = -1;
+        if (tr && threadIdx.x == 64) { pf_delay += t0 - t_pend; pf_total += clock64() - t0; pf_n += 1; }
+      }
     };
     for (;;) {
       if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) flush_pend();
@@ -506,9 +548,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (ly.epi == PEPI_STORE) {
         // ---- bias + LeakyReLU -> bf16 -> swizzled staging tile -> global (TMA store, or transposed st.global)
         const bool tp = tr && threadIdx.x == 64;
-        long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+        long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0, tq6 = 0;
         const float slope = p.slope;
-        const float* const bias_tile = ly.bias + n0;
+        const float* const bias_tile = sbias + ly.bias_off + n0;  // shared memory (the host guarantees bias_off >= 0)
         const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
         // 32-column TMEM loads, software pipelined: the next load is in flight while the previous one is converted
         uint32_t va[32], vb[32];
@@ -524,17 +566,27 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           tmem_ld_wait();
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, vb);
           if (tp) tq2 = clock64();
+          {
+            float4 bq[8];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float4 ba = __ldg(b4 + 2 * t), bb = __ldg(b4 + 2 * t + 1);
-            uint4 w;
-            w.x = bias_leaky_pack(va[8 * t + 0], va[8 * t + 1], ba.x, ba.y, slope);
-            w.y = bias_leaky_pack(va[8 * t + 2], va[8 * t + 3], ba.z, ba.w, slope);
-            w.z = bias_leaky_pack(va[8 * t + 4], va[8 * t + 5], bb.x, bb.y, slope);
-            w.w = bias_leaky_pack(va[8 * t + 6], va[8 * t + 7], bb.z, bb.w, slope);
-            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
+            for (int t = 0; t < 8; ++t) bq[t] = b4[t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float4 ba = bq[2 * t], bb = bq[2 * t + 1];
+              uint4 w;
+              w.x = bias_leaky_pack(va[8 * t + 0], va[8 * t + 1], ba.x, ba.y, slope);
+              w.y = bias_leaky_pack(va[8 * t + 2], va[8 * t + 3], ba.z, ba.w, slope);
+              w.z = bias_leaky_pack(va[8 * t + 4], va[8 * t + 5], bb.x, bb.y, slope);
+              w.w = bias_leaky_pack(va[8 * t + 6], va[8 * t + 7], bb.z, bb.w, slope);
+              *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
+            }
           }
+          float4 bq[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) bq[t] = b4[8 + t];   // in flight across the TMEM wait
+          if (tp) tq5 = clock64();
           tmem_ld_wait();
+          if (tp) tq6 = clock64();
           if (c + 2 < n_chunks) {
             tmem_ld_32x32_ptr(taddr + (c + 2) * 64, va);
           } else {  // this warp's last read of the accumulator stage
@@ -544,7 +596,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float4 ba = __ldg(b4 + 8 + 2 * t), bb = __ldg(b4 + 8 + 2 * t + 1);
+            const float4 ba = bq[2 * t], bb = bq[2 * t + 1];
             uint4 w;
             w.x = bias_leaky_pack(vb[8 * t + 0], vb[8 * t + 1], ba.x, ba.y, slope);
             w.y = bias_leaky_pack(vb[8 * t + 2], vb[8 * t + 3], ba.z, ba.w, slope);
@@ -571,14 +623,18 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             }
           }
           buf ^= 1;
-          if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; }
+          if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; ph_m1 += tq5 - tq2; ph_w2 += tq6 - tq5; }
         }
         if (half >= n_chunks) {  // narrow tile: this warp had no chunk, still has to release the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
-        if (p.store_mode == 0) { pend_kind = ly.out_kind; pend_rb = rb; }
+        if (p.store_mode == 0) {
+          pend_kind = ly.out_kind; pend_rb = rb;
+          if (tr && threadIdx.x == 64) t_pend = clock64();
+          if (!pushing) flush_pend();  // small batch: the hand-off latency is on the critical path, do not defer it
+        }
         else p2_arrive(p, ly.out_kind, rb, lane, false);
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
@@ -590,8 +646,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
-          const float4* b4 = reinterpret_cast<const float4*>(ly.bias + n0 + c * 64);
-          const float4* w4 = reinterpret_cast<const float4*>(p.w3 + n0 + c * 64);
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + ly.bias_off + n0 + c * 64);
+          const float4* w4 = reinterpret_cast<const float4*>(sbias + p.w3_off + n0 + c * 64);
           tmem_ld_wait();
           if (c + 2 >= n_chunks) {
             tc_fence_before();
@@ -601,7 +657,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           float rowdot = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 b = __ldg(b4 + j), w = __ldg(w4 + j);
+            const float4 b = b4[j], w = w4[j];
             rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 0]) + b.x, slope), w.x, rowdot);
             rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 1]) + b.y, slope), w.y, rowdot);
             rowdot = fmaf(leaky_max(__uint_as_float(v[4 * j + 2]) + b.z, slope), w.z, rowdot);
@@ -651,7 +707,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
-          const float4* b4 = reinterpret_cast<const float4*>(ly.bias + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(sbias + ly.bias_off + col0);
           tmem_ld_wait();
           if (c + 2 >= n_chunks) {
             tc_fence_before();
@@ -661,7 +717,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           float* f = reinterpret_cast<float*>(v);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float4 b = __ldg(b4 + j);
+            const float4 b = b4[j];
             f[4 * j + 0] = tanh_fast(f[4 * j + 0] + b.x);
             f[4 * j + 1] = tanh_fast(f[4 * j + 1] + b.y);
             f[4 * j + 2] = tanh_fast(f[4 * j + 2] + b.z);
@@ -772,6 +828,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     if (tr && threadIdx.x == 64) {
       tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
       tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
+      tr[251] = ph_m1; tr[252] = ph_w2;
+      tr[245] = pf_delay; tr[246] = pf_wait; tr[247] = pf_total; tr[248] = pf_n;
     }
   }
 
@@ -797,7 +855,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.fin[k * p.rb_cap + i] = 0;
     for (int i = threadIdx.x; i < p.n_total - p.n_static; i += blockDim.x) p.queue[i] = 0ull;
     if (threadIdx.x == 0) { p.sched->q_head = 0; p.sched->q_tail = 0; p.sched->p0_next = 0; p.sched->init = 0; p.sched->done = 0; }
-    if (tr && threadIdx.x == 0) tr[13] = clock64();
+    if (tr && threadIdx.x == 0) { tr[13] = clock64(); tr[253] = static_cast<long long>(globaltimer_ns()); }
   }
 }
 

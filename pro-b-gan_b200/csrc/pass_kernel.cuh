@@ -116,6 +116,14 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(int* p, int v) {
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atom_relaxed_gpu_add(int* p, int v) {
+  int old;
+  asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ int atom_release_gpu_add(int* p, int v) {
   int old;
   asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

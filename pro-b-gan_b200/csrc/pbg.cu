@@ -377,7 +377,12 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
 
   if (bf) {
-    static const bool use_v1 = [] { const char* e = getenv("PBG_PASS_V1"); return e && atoi(e) != 0; }();
+    static const bool force_v1 = [] { const char* e = getenv("PBG_PASS_V1"); return e && atoi(e) != 0; }();
+    // the pair kernel keeps every bias in shared memory; wider models take the single-CTA kernel
+    int bias_floats = 0;
+    if (a.run_g) bias_floats += c->g[0].np + c->g[1].np + c->g[2].np;
+    if (a.run_d) bias_floats += c->d[0].np + 2 * c->d[1].np;
+    const bool use_v1 = force_v1 || bias_floats > P2Smem::kBiasFloats;
     return use_v1 ? launch_pass(c, w, a, gp, off, rows, gen_out, scores)
                   : launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
   } else {
@@ -474,7 +479,8 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   static bool attr_set = false;
   static int attr_dev = -1;
   if (!attr_set || attr_dev != c->dims.device) {
-    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
+    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
+    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
     attr_set = true; attr_dev = c->dims.device;
   }
   const int grid = pass_grid(c) & ~1;  // whole pairs
@@ -499,9 +505,17 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     p.tm_a[k] = *amap[k];
     p.tm_w[k] = bn == 256 ? l.tmap_w128 : l.tmap_w64;
     if (omap[k]) p.tm_o[k] = *omap[k];
-    p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], ldos[k], l.b_pad, outs[k]};
+    p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], ldos[k], -1, l.b_pad, outs[k]};
     p.layer_mask |= 1u << k;
     total += static_cast<long long>(nrb) * (l.np / bn);
+  }
+  // biases + final dot weights are copied to shared memory at kernel start (pass2_fits checked that they fit)
+  {
+    int off = 0;
+    for (int k = 0; k < 5; ++k) if (on[k]) { p.layer[k].bias_off = off; off += lin[k]->np; }
+    p.w3_off = off;
+    if (on[IT_D_L1]) off += lin[IT_D_L1]->np;
+    if (off > P2Smem::kBiasFloats) return fail(c, PBG_ERR_INVALID, "internal: biases do not fit the pair kernel's shared memory");
   }
   if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
@@ -552,11 +566,12 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
-    pbg_pass2_kernel<<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p); }
+    if (p.trace) pbg_pass2_kernel<true><<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p);
+    else pbg_pass2_kernel<false><<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p); }
   const cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, pbg_pass2_kernel);
+    cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false>);
     return fail(c, PBG_ERR_CUDA, "pass kernel launch failed: %s (grid %d x %d threads, %d regs/thread, %zu B static + %d B dynamic smem, "
                 "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kPassThreads, fa.numRegs,
                 fa.sharedSizeBytes, P2Smem::kTotal, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);

@@ -73,6 +73,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 #ifndef PBG_HANG_GUARD
 #define PBG_HANG_GUARD 1
 #endif
+// Cold path of every guarded wait: kept out of line so that the waits stay a few instructions each.
+__device__ __noinline__ void pbg_wait_timed_out(const char* what, uint32_t a, uint32_t b) {
+  printf("pbg: %s wait timed out (block %d thread %d: %u %u)\n", what, blockIdx.x, threadIdx.x, a, b);
+  __trap();
+}
 // Blocking wait.  try_wait suspends the thread in hardware until the phase completes or a time limit expires, so
 // the loop body runs rarely; with PBG_HANG_GUARD a wait that keeps failing for millions of rounds traps instead
 // of hanging the GPU (a protocol bug must never cost a box).  The guard is a register counter: no clock reads.
@@ -80,11 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if PBG_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 4000000u) {
-      printf("pbg: mbarrier wait timed out (block %d thread %d parity %u barrier @%u)\n", blockIdx.x, threadIdx.x, parity,
-             smem_u32(bar) & 0x3ffu);
-      __trap();
-    }
+    if (++spins > 4000000u) pbg_wait_timed_out("mbarrier (parity, offset)", parity, smem_u32(bar) & 0x3ffu);
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
@@ -247,10 +248,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 #if PBG_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > 4000000u) {
-      printf("pbg: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (++spins > 4000000u) pbg_wait_timed_out("cluster mbarrier (parity, offset)", parity, smem_u32(bar) & 0x3ffu);
   }
 #else
   while (!mbar_try_wait_cluster(bar, parity)) {

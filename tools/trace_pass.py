@@ -60,11 +60,22 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     P(f"   producer: dep wait {hdr[:, 11].mean():.0f} (max {hdr[:, 11].max():.0f})  empty wait {hdr[:, 1].mean():.0f}")
     P(f"   mma: full wait {hdr[:, 3].mean():.0f} (max {hdr[:, 3].max():.0f})  tmem wait {hdr[:, 4].mean():.0f}")
     P(f"   epilogue warp 2: acc wait {hdr[:, 7].mean():.0f}  busy {hdr[:, 10].mean():.0f}")
-    ph = t[:, 240:246]
+    ph = t[:, 240:256]
     nchunk = ph[:, 3].clamp_min(1); ntile = ph[:, 5].clamp_min(1)
     P(f"   mma: waiting for an item {hdr[:, 15][hdr[:, 9] > 0].mean():.0f}")
     P(f"   STORE epilogue phases (warp 2, clk per 64-col chunk): staging free {(ph[:, 4] / nchunk).mean():.0f}  tmem ld+wait {(ph[:, 0] / nchunk).mean():.0f}"
       f"  bias+math+STS {(ph[:, 1] / nchunk).mean():.0f}  store {(ph[:, 2] / nchunk).mean():.0f}")
+    P(f"      of bias+math+STS: first half math {(ph[:, 11] / nchunk).mean():.0f}  second TMEM wait {(ph[:, 12] / nchunk).mean():.0f}")
+    if ph[:, 13].max() > 0:
+        P(f"   kernel body (globaltimer): first CTA entry -> roles start {(hdr[:, 14].min() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f} us (entry skew {(ph[:, 14].max() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f}),"
+          f" -> last epilogue end ~{(hdr[:, 8] - hdr[:, 0]).max() / 1.92e3:.2f} us later, -> counters reset at {(ph[:, 13].max() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f} us")
+    pfn = ph[:, 8].clamp_min(1)
+    P(f"   deferred arrival (warp 2, clk per tile): epilogue end -> flush {(ph[:, 5] / pfn).mean():.0f}  bulk-store completion wait {(ph[:, 6] / pfn).mean():.0f}"
+      f"  whole flush {(ph[:, 7] / pfn).mean():.0f}")
+    gsel = ph[:, 9] > 0
+    if gsel.any():
+        P(f"   phase-0 gather (warp 2): start@ {(ph[:, 9] - hdr[:, 0])[gsel].mean():.0f}  loads+stores issued@ {(ph[:, 10] - hdr[:, 0])[gsel].mean():.0f}"
+          f"  arrived@ {(hdr[:, 5] - hdr[:, 0])[gsel].mean():.0f}")
     kind = raw0 & 0xff
     mblk = (raw0 >> 8) & 0xfff
     valid = raw0 != 0
