@@ -239,7 +239,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* sched_full = tmem_empty + 2;
   uint64_t* sched_empty = sched_full + kP2Ring;
-  uint2* ring = reinterpret_cast<uint2*>(sched_empty + kP2Ring);
+  uint64_t* bias_bar = sched_empty + kP2Ring;
+  uint2* ring = reinterpret_cast<uint2*>(bias_bar + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + kP2Ring);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
   float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
@@ -272,19 +273,21 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       mbar_init(&sched_full[s], 1);                 // the scheduler (local + remote arrive)
       mbar_init(&sched_empty[s], kRingConsumers);   // peer's (the scheduler's CTA)
     }
+    mbar_init(bias_bar, 1);
     fence_mbar_init();
-  }
-  // Biases (and the final dot weights) live in shared memory for the whole launch: with ~224 KB of the SM carved out
-  // as shared memory there is next to no L1 left, so a bias read through the global path costs an L2 round trip.
-  for (int k = 0; k < 5; ++k) {
-    if ((p.layer_mask & (1u << k)) && p.layer[k].bias_off >= 0) {
-      const int n = p.layer[k].n_tiles * p.layer[k].block_n;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) sbias[p.layer[k].bias_off + i] = __ldg(p.layer[k].bias + i);
-    }
-  }
-  if ((p.layer_mask & (1u << IT_D_L1)) && p.w3_off >= 0) {
-    const int n = p.layer[IT_D_L1].n_tiles * p.layer[IT_D_L1].block_n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sbias[p.w3_off + i] = __ldg(p.w3 + i);
+    // Biases (and the final dot weights) live in shared memory for the whole launch: with ~224 KB of the SM carved out
+    // as shared memory a bias read through the global path is an L2 round trip.  One bulk copy per array, in flight
+    // while the rest of the prologue and the gather run; the epilogue warps wait for them once.
+    uint32_t bytes = 0;
+    for (int k = 0; k < 5; ++k)
+      if (p.layer_mask & (1u << k)) bytes += static_cast<uint32_t>(p.layer[k].n_tiles * p.layer[k].block_n) * 4u;
+    if (p.layer_mask & (1u << IT_D_L1)) bytes += static_cast<uint32_t>(p.layer[IT_D_L1].n_tiles * p.layer[IT_D_L1].block_n) * 4u;
+    mbar_arrive_expect_tx(bias_bar, bytes);
+    for (int k = 0; k < 5; ++k)
+      if (p.layer_mask & (1u << k))
+        bulk_load_1d(sbias + p.layer[k].bias_off, p.layer[k].bias, static_cast<uint32_t>(p.layer[k].n_tiles * p.layer[k].block_n) * 4u, bias_bar);
+    if (p.layer_mask & (1u << IT_D_L1))
+      bulk_load_1d(sbias + p.w3_off, p.w3, static_cast<uint32_t>(p.layer[IT_D_L1].n_tiles * p.layer[IT_D_L1].block_n) * 4u, bias_bar);
   }
   if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
@@ -479,6 +482,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     // the block's counter) where this warp would otherwise idle -- while its next TMEM load is in flight, or before
     // it blocks on the ring / an accumulator that is not ready yet.  It is never postponed past a point where the
     // warp can block indefinitely: the item it would wait for may depend on exactly this arrival.
+    mbar_wait(bias_bar, 0);  // biases have landed (issued in the prologue)
     long long pf_delay = 0, pf_wait = 0, pf_total = 0, pf_n = 0, t_pend = 0;
     auto flush_pend = [&]() {
       if (pend_kind >= 0) {
@@ -698,6 +702,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       } else {
         // ---- PEPI_TANH: bias + tanh -> generator output (fp32 / bf16), optional cosine vs the tail embedding
         flush_pend();
+        const bool tpt = tr && threadIdx.x == 64;
+        if (tpt) tr[232] = clock64();
         const bool want_out = p.gen_out != nullptr;
         const bool in_cta = ly.n_tiles == 1 && n_chunks == 2;  // the whole output row lives in this quarter's two warps
         float* part = p.part_g + (static_cast<size_t>(rb) * p.slots_g) * 3 * kP2Rows;
@@ -715,6 +721,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
           }
           float* f = reinterpret_cast<float*>(v);
+          if (tpt) tr[233] = clock64();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float4 b = b4[j];
@@ -723,6 +730,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             f[4 * j + 2] = tanh_fast(f[4 * j + 2] + b.z);
             f[4 * j + 3] = tanh_fast(f[4 * j + 3] + b.w);
           }
+          if (tpt) tr[234] = clock64();
           if (want_cos) {
             // tail pieces are in the staging tile: one row per lane
             float cs_dot = 0.f, cs_pp = 0.f, cs_tt = 0.f;
@@ -757,6 +765,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
               mine[2 * kP2Rows + row_in_blk] = cs_tt;
             }
           }
+          if (tpt) tr[235] = clock64();
           if (want_out && col0 < p.n_valid) {
             const long long grow0 = static_cast<long long>(rb) * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
             if (p.out_f32) {
@@ -802,6 +811,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
+        if (tpt) tr[236] = clock64();
         if (want_cos && !in_cta) {
           const int old = warp_publish_fetch(p.fin + FIN_G * p.rb_cap + rb, lane);
           if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
@@ -843,7 +853,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   }
   // the last CTA to finish re-arms the scheduler and zeroes the arrival counters for the next launch
   if (threadIdx.x == 0) {
-    __threadfence();
     const int old = atomicAdd(&p.sched->done, 1);
     *last_flag = (old == static_cast<int>(gridDim.x) - 1);
   }

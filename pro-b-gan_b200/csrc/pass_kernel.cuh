@@ -39,7 +39,7 @@ constexpr int kSchedRing = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kPassThreads = 64 + 32 * kEpiWarps;
 constexpr int kTraceSlots = 256;                      // diagnostics slots per CTA (pbg_debug_trace)
-constexpr int kTraceItems = 56;                       // slots 16 .. 239; slots 240 .. 255: epilogue phase sums
+constexpr int kTraceItems = 54;                       // slots 16 .. 231; 232 .. 239 and 240 .. 255: epilogue phase stamps / sums
 constexpr int kGatherRows = 32;                       // rows per gather item
 constexpr int kGatherPerBlock = kBlockM / kGatherRows;  // gather items per 128-row block
 

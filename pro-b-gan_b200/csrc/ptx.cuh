@@ -114,6 +114,11 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tma
       "l"(hint)
       : "memory");
 }
+// 1-D bulk copy global -> shared (bytes: multiple of 16, both addresses 16-byte aligned), completing on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // 2-D tiled store smem -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

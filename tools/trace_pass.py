@@ -69,6 +69,11 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     if ph[:, 13].max() > 0:
         P(f"   kernel body (globaltimer): first CTA entry -> roles start {(hdr[:, 14].min() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f} us (entry skew {(ph[:, 14].max() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f}),"
           f" -> last epilogue end ~{(hdr[:, 8] - hdr[:, 0]).max() / 1.92e3:.2f} us later, -> counters reset at {(ph[:, 13].max() - ph[:, 14][ph[:, 14] > 0].min()) / 1e3:.2f} us")
+    tsel = t[:, 236] > 0
+    if tsel.any():
+        tt = t[tsel]
+        P(f"   TANH epilogue (warp 2, last tile): start -> tmem loaded {(tt[:, 233] - tt[:, 232]).mean():.0f}  tanh {(tt[:, 234] - tt[:, 233]).mean():.0f}"
+          f"  cosine {(tt[:, 235] - tt[:, 234]).mean():.0f}  output {(tt[:, 236] - tt[:, 235]).mean():.0f}")
     pfn = ph[:, 8].clamp_min(1)
     P(f"   deferred arrival (warp 2, clk per tile): epilogue end -> flush {(ph[:, 5] / pfn).mean():.0f}  bulk-store completion wait {(ph[:, 6] / pfn).mean():.0f}"
       f"  whole flush {(ph[:, 7] / pfn).mean():.0f}")
@@ -79,6 +84,7 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     kind = raw0 & 0xff
     mblk = (raw0 >> 8) & 0xfff
     valid = raw0 != 0
+    valid[:, 54:] = False
     claim_r = (((raw0 >> 20) - (ti64[:, 0:1] & ((1 << 43) - 1))) & ((1 << 43) - 1)).double()  # clock64 << 20 keeps 43 bits
     for k, name in KIND.items():
         sel = valid & (kind == k)
