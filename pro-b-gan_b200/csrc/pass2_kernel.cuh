@@ -72,7 +72,6 @@ struct alignas(64) Pass2Params {
   int n_static;         // tickets served from the segment table; pushes are disabled when n_static == n_total
   int n_seg;
   P2Segment seg[8];
-  int store_mode;       // PEPI_STORE: 0 = TMA store from the staging tile, 1 = staged transposes + coalesced st.global
   int nrb;              // 256-row blocks in this pass
   int rb_cap;           // stride of the counter arrays
   int M;                // rows in this pass
@@ -209,7 +208,7 @@ __device__ __forceinline__ void p2_stage_tail(uint8_t* st, unsigned long long tr
     const int r = i * 2 + (lane >> 4), t = lane & 15;
     const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
     tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tp2 != nullptr && col0 + t * 4 < n_valid) tv[i] = __ldg(reinterpret_cast<const float4*>(tp2 + col0 + t * 4));
+    if (tp2 != nullptr && col0 + t * 4 < n_valid) tv[i] = ld_stream4(tp2 + col0 + t * 4);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -227,7 +226,8 @@ constexpr uint32_t kItemPoll = 1u << 16;   // ring item flag: the producers poll
 __device__ __forceinline__ uint32_t ring_dep(uint2 it) { return (it.x >> 24) << 3; }
 
 // TR: the diagnostics instance (pbg_debug_trace); the production instance carries no trace code or registers.
-template <bool TR>
+// FASTG: the gather only carries the E = 128, Z <= 128 register path (the host checks the dims).
+template <bool TR, bool FASTG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPassThreads, 1)
 pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   using L = P2Smem;
@@ -251,6 +251,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const long long t_entry = (TR && p.trace && threadIdx.x == 0) ? static_cast<long long>(globaltimer_ns()) : 0;
+  // Programmatic dependent launch: the next pass may start its prologue while this one is still running ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int kRingConsumers = 2 * (1 + kEpiWarps) + 1;  // both producers, the MMA issuer, 16 epilogue warps
 
   if (threadIdx.x == 0) {
@@ -294,6 +296,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  // ... and this pass waits here, prologue done, until the previous grid (which shares the workspace, the counters
+  // and the scheduler) has completed.  Everything above touches only this CTA and the immutable weights.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   long long* const tr = (TR && p.trace) ? p.trace + kTraceSlots * blockIdx.x : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); tr[254] = t_entry; }
@@ -307,20 +312,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   if (pushing && blockIdx.x == 0 && threadIdx.x == 0) {
     for (int rb = p.p0_blocks; rb < min(p.nrb, p.p0_blocks + p.gather_ahead); ++rb) p2_push_gather(p, rb);
   }
-  // ---- phase 0: the epilogue warps of all CTAs gather the first row blocks, one 4-row group per warp and round
-  //      (static assignment: no claim atomics); warps 0 / 1 go straight to their roles
-  if (warp >= 2) {
-    const int gw = static_cast<int>(blockIdx.x) * kEpiWarps + (warp - 2);
-    const int gstep = static_cast<int>(gridDim.x) * kEpiWarps;
-    for (int g = gw; g < p.phase0_groups; g += gstep) {
-      if (tr && threadIdx.x == 64) tr[249] = clock64();
-      pass_gather_group(p.gather, g, lane);
-      if (tr && threadIdx.x == 64) tr[250] = clock64();
-      p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
-    }
-    if (tr && threadIdx.x == 64) tr[5] = clock64();
-  }
-
   if (warp == 1 && !leader) {
     // ------------------------------------------------------------ scheduler (one thread of the peer CTA)
     if (lane == 0) {
@@ -492,27 +483,45 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (tr && threadIdx.x == 64) { pf_delay += t0 - t_pend; pf_total += clock64() - t0; pf_n += 1; }
       }
     };
+    // phase 0: before it looks at the ring, this warp gathers its share of the first row blocks, one 4-row group per
+    // round (static assignment over all epilogue warps of the grid: no claim atomics)
+    int p0g = static_cast<int>(blockIdx.x) * kEpiWarps + wep;
+    const int p0step = static_cast<int>(gridDim.x) * kEpiWarps;
     for (;;) {
-      if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) flush_pend();
-      mbar_wait(&sched_full[slot], sphase);
-      const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
-      if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
-      const int kind = it.x & 0xff;
-      if (kind == IT_END) { flush_pend(); break; }
+      long long group = -1;   // >= 0: a gather group to do in this iteration (phase 0 or a gather item)
+      int g_rb = 0;
+      uint2 it = make_uint2(IT_GATHER, 0u);
+      int kind = IT_GATHER;
+      if (p0g < p.phase0_groups) {
+        group = p0g; g_rb = p0g / kP2GroupsPerBlock; p0g += p0step;
+        if (tr && threadIdx.x == 64) tr[249] = clock64();
+      } else {
+        if (tr && threadIdx.x == 64 && tr[5] == 0) tr[5] = clock64();
+        if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) flush_pend();
+        mbar_wait(&sched_full[slot], sphase);
+        it = ld_cluster_u32x2(ring_addr + slot * 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
+        if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+        kind = it.x & 0xff;
+        if (kind == IT_END) { flush_pend(); break; }
+        if (kind == IT_GATHER) {
+          ++item_no;  // the producer numbers gather items too
+          g_rb = static_cast<int>(it.y);
+          group = static_cast<long long>(g_rb) * kP2GroupsPerBlock + ((it.x >> 8) & 0xff) * kP2WarpsPerPair + rank * kEpiWarps + wep;
+        }
+      }
+      if (group >= 0) {
+        flush_pend();
+        pass_gather_group<FASTG ? 1 : 2>(p.gather, group, lane);
+        if (tr && threadIdx.x == 64) tr[250] = clock64();
+        p2_arrive(p, DEP_X, g_rb, lane, false);
+        continue;
+      }
       const int n_blk = (it.x >> 8) & 0xff;
       const int rb = static_cast<int>(it.y);
       long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
       ++item_no;
-      if (kind == IT_GATHER) {
-        flush_pend();
-        if (ti) ti[2] = clock64();
-        pass_gather_group(p.gather, static_cast<long long>(rb) * kP2GroupsPerBlock + n_blk * kP2WarpsPerPair + rank * kEpiWarps + wep, lane);
-        p2_arrive(p, DEP_X, rb, lane, false);
-        if (ti) ti[3] = clock64();
-        continue;
-      }
       const P2Layer& ly = p.layer[kind];
       const long long grow = static_cast<long long>(rb) * kP2Rows + row_in_blk;
       const bool row_ok = grow < p.M;
@@ -524,12 +533,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       // row pieces of this warp's first chunk, coalesced, into the staging tile
       const bool want_cos = ly.epi == PEPI_TANH && p.cosine != nullptr;
       unsigned long long trow_bits = 0ull;
-      if (ly.epi == PEPI_TANH) {
+      if (want_cos) {
         // the staging tile may still be the source of an activation store issued by an earlier tile of this warp
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-      }
-      if (want_cos) {
         const float* trow = nullptr;
         if (row_ok) {
           long long tid = p.tail_idx[grow * p.tail_stride];
@@ -546,6 +553,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (tr && lane == 0) { w_acc += clock64() - t; }
         if (ti) ti[2] = clock64();
       }
+      flush_pend();  // (no-op if done above) the previous tile's stores have had a whole accumulator wait to complete
       const long long t_busy0 = (tr && lane == 0) ? clock64() : 0;
       tc_fence_after();
 
@@ -558,13 +566,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
         // 32-column TMEM loads, software pipelined: the next load is in flight while the previous one is converted
         uint32_t va[32], vb[32];
-        flush_pend();  // the previous tile's stores have had a whole accumulator wait to complete
         if (half < n_chunks) tmem_ld_32x32_ptr(taddr + half * 64, va);
         for (int c = half; c < n_chunks; c += 2) {
           if (tp) tq0 = clock64();
           const float4* b4 = reinterpret_cast<const float4*>(bias_tile + c * 64);
           // this staging buffer is free once the bulk store issued two chunks ago has read it
-          if (p.store_mode == 0) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
           if (tp) tq1 = clock64();
           uint8_t* sbuf = st + buf * 4096;
           tmem_ld_wait();
@@ -609,22 +617,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((4 + t) ^ (lane & 7)) << 4)) = w;
           }
           if (tp) tq3 = clock64();
-          if (p.store_mode == 0) {
-            fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
-              tma_store_commit();
-            }
-          } else {
-            __syncwarp();
-            __nv_bfloat16* obase = ly.out + static_cast<size_t>(row0) * ly.ldo + n0 + c * 64;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = i * 4 + (lane >> 3), t = lane & 7;
-              const uint4 w = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((t ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(r) * ly.ldo + t * 8) = w;
-            }
+          fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
+            tma_store_commit();
           }
           buf ^= 1;
           if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; ph_m1 += tq5 - tq2; ph_w2 += tq6 - tq5; }
@@ -634,17 +631,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
-        if (p.store_mode == 0) {
-          pend_kind = ly.out_kind; pend_rb = rb;
-          if (tr && threadIdx.x == 64) t_pend = clock64();
-          if (!pushing) flush_pend();  // small batch: the hand-off latency is on the critical path, do not defer it
-        }
-        else p2_arrive(p, ly.out_kind, rb, lane, false);
+        pend_kind = ly.out_kind; pend_rb = rb;
+        if (tr && threadIdx.x == 64) t_pend = clock64();
+        if (!pushing) flush_pend();  // small batch: the hand-off latency is on the critical path, do not defer it
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block
         const float slope = p.slope;
-        flush_pend();
         float* part = p.part_d + (static_cast<size_t>(rb) * p.slots_d) * kP2Rows;
         for (int c = half; c < n_chunks; c += 2) {
           uint32_t v[64];
@@ -701,7 +694,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         }
       } else {
         // ---- PEPI_TANH: bias + tanh -> generator output (fp32 / bf16), optional cosine vs the tail embedding
-        flush_pend();
         const bool tpt = tr && threadIdx.x == 64;
         if (tpt) tr[232] = clock64();
         const bool want_out = p.gen_out != nullptr;
@@ -766,24 +758,16 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             }
           }
           if (tpt) tr[235] = clock64();
-          if (want_out && col0 < p.n_valid) {
-            const long long grow0 = static_cast<long long>(rb) * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
+          if (want_out && row_ok) {
+            // one row per lane, 16-byte stores (2 MB for a 4096-row pass: not worth a transpose through shared memory)
             if (p.out_f32) {
+              float* orow = static_cast<float*>(p.gen_out) + grow * p.ld_gen + col0;
 #pragma unroll
               for (int t = 0; t < 16; ++t)
-                *reinterpret_cast<float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4)) =
-                    make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
-              __syncwarp();
-              float* obase = static_cast<float*>(p.gen_out) + col0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int r = i * 2 + (lane >> 4), t = lane & 15;
-                const float4 x = *reinterpret_cast<const float4*>(st + r * 256 + ((t ^ (r & 7)) << 4));
-                const long long gr = grow0 + r;
-                if (gr < p.M && col0 + t * 4 < p.n_valid) *reinterpret_cast<float4*>(obase + gr * p.ld_gen + t * 4) = x;
-              }
+                if (col0 + t * 4 < p.n_valid)
+                  *reinterpret_cast<float4*>(orow + t * 4) = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
             } else {
-              // bf16: 64 columns = 128 B per row, 8 x 16-byte pieces, swizzled by row & 7
+              __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.gen_out) + grow * p.ld_gen + col0;
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
                 uint4 w;
@@ -791,19 +775,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
                 w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
                 w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
-                *reinterpret_cast<uint4*>(st + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
-              }
-              __syncwarp();
-              __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(p.gen_out) + col0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int r = i * 4 + (lane >> 3), t = lane & 7;
-                const uint4 w = *reinterpret_cast<const uint4*>(st + r * 128 + ((t ^ (r & 7)) << 4));
-                const long long gr = grow0 + r;
-                if (gr < p.M && col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(obase + gr * p.ld_gen + t * 8) = w;
+                if (col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(orow + t * 8) = w;
               }
             }
-            __syncwarp();
           }
         }
         if (half >= n_chunks) {

@@ -156,6 +156,8 @@ __device__ __forceinline__ float leaky_max(float x, float slope) { return fmaxf(
 // One warp gathers a group of 4 consecutive rows: indices first, then every row load in flight, then the stores.
 // A gather item is 32 rows = 8 groups (one per epilogue warp); the first row blocks of a pass are gathered by all
 // warps of all CTAs before the roles start (phase 0), one group per warp.
+// MODE 0: both layouts behind a run-time test; 1: only the E = 128, Z <= 128 register path; 2: only the generic loop
+template <int MODE = 0>
 __device__ __forceinline__ void pass_gather_group(const GatherParams& g, long long group, int lane) {
   const long long r0 = group * 4;
   __nv_bfloat16* xg = static_cast<__nv_bfloat16*>(g.xg);
@@ -182,7 +184,7 @@ __device__ __forceinline__ void pass_gather_group(const GatherParams& g, long lo
   if (bad) atomicOr(g.err_flag, 1);
   const unsigned long long sp = reinterpret_cast<unsigned long long>(src);
   const int E4 = g.E >> 2, Z4 = g.Z >> 2;
-  if (E4 == 32 && Z4 <= 32) {
+  if (MODE == 1 || (MODE == 0 && E4 == 32 && Z4 <= 32)) {
     float4 hv[4], rv[4], tv[4], zv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

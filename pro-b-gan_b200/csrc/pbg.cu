@@ -473,16 +473,27 @@ int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp,
   return PBG_OK;
 }
 
+template <bool TR, bool FASTG>
+cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s, bool pdl) {
+  auto kern = pbg_pass2_kernel<TR, FASTG>;
+  static int attr_dev = -1;  // per instantiation; ctxs on different devices share the function handle
+  if (attr_dev != c->dims.device) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_dev = c->dims.device;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPassThreads); cfg.dynamicSmemBytes = P2Smem::kTotal; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 // The pair kernel (pass2_kernel.cuh): 256-row blocks, tiles of 256 x {256 | 128}, one CTA pair per tile.
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
                  void* gen_out, float* scores) {
-  static bool attr_set = false;
-  static int attr_dev = -1;
-  if (!attr_set || attr_dev != c->dims.device) {
-    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
-    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal));
-    attr_set = true; attr_dev = c->dims.device;
-  }
   const int grid = pass_grid(c) & ~1;  // whole pairs
   Pass2Params p;
   memset(&p, 0, sizeof p);
@@ -545,8 +556,6 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   }
   p.n_total = static_cast<int>(total);
   if (total - p.n_static > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
-  static const int store_env = [] { const char* e = getenv("PBG_STORE_MODE"); return e ? atoi(e) : 0; }();
-  p.store_mode = store_env;
   p.gather = gp;
   static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
   p.poll_ns = poll_env;
@@ -565,13 +574,17 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.probs = a.probs ? a.probs + off : nullptr;
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
+  // programmatic dependent launch: this pass may begin its prologue while the previous kernel of the stream drains
+  static const bool pdl = [] { const char* e = getenv("PBG_PDL"); return !e || atoi(e) != 0; }();
+  const bool fastg = c->dims.embed_dim == 128 && c->dims.noise_dim % 4 == 0 && c->dims.noise_dim <= 128;
+  cudaError_t le;
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
-    if (p.trace) pbg_pass2_kernel<true><<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p);
-    else pbg_pass2_kernel<false><<<grid, kPassThreads, P2Smem::kTotal, a.stream>>>(p); }
-  const cudaError_t le = cudaGetLastError();
+    if (p.trace) le = fastg ? launch_p2<true, true>(c, p, grid, a.stream, pdl) : launch_p2<true, false>(c, p, grid, a.stream, pdl);
+    else le = fastg ? launch_p2<false, true>(c, p, grid, a.stream, pdl) : launch_p2<false, false>(c, p, grid, a.stream, pdl); }
+  if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false>);
+    cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false, true>);
     return fail(c, PBG_ERR_CUDA, "pass kernel launch failed: %s (grid %d x %d threads, %d regs/thread, %zu B static + %d B dynamic smem, "
                 "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kPassThreads, fa.numRegs,
                 fa.sharedSizeBytes, P2Smem::kTotal, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
