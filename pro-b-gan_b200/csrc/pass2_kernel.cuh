@@ -35,7 +35,7 @@
 
 namespace pbg {
 
-constexpr int kP2Stages = 4;
+constexpr int kP2Stages = 5;
 constexpr int kP2Ring = 4;
 constexpr int kP2Rows = 256;                        // rows of one pair tile = one dependency block
 constexpr int kP2GroupsPerBlock = kP2Rows / 4;      // 4-row gather groups per block
@@ -55,7 +55,7 @@ struct P2Layer {
   __nv_bfloat16* out;// PEPI_STORE: next layer's A operand
 };
 
-struct P2Segment { int kind, n_tiles, start, count; };  // static tickets [start, start + count): (kind, n = i % n_tiles, rb = i / n_tiles)
+struct P2Segment { int kind, n_tiles, start, rb0; };  // static tickets from `start` up to the next segment: (kind, n = i % n_tiles, rb = rb0 + i / n_tiles)
 
 struct alignas(64) Pass2Params {
   CUtensorMap tm_a[5];  // A operand of layer i: xg0, xd0, actG0, actD0, actG1   (box 64 x 128 rows, SWIZZLE_128B)
@@ -71,7 +71,7 @@ struct alignas(64) Pass2Params {
   int n_total;          // items this launch pops in total (static + pushed)
   int n_static;         // tickets served from the segment table; pushes are disabled when n_static == n_total
   int n_seg;
-  P2Segment seg[8];
+  P2Segment seg[16];
   int nrb;              // 256-row blocks in this pass
   int rb_cap;           // stride of the counter arrays
   int M;                // rows in this pass
@@ -98,7 +98,7 @@ struct P2Smem {
   static constexpr int kW = 128 * kBlockK * 2;   // this CTA's half of a 256-wide W tile
   static constexpr int kStage = kA + kW;
   static constexpr int kStagingOff = kP2Stages * kStage;
-  static constexpr int kStagingPerWarp = 8192;   // two 4 KB store tiles / one 32 x 64 fp32 transpose tile
+  static constexpr int kStagingPerWarp = 4096;   // one 32 x 64 bf16 store tile / one 32 x 32 fp32 transpose tile
   static constexpr int kBiasOff = kStagingOff + kEpiWarps * kStagingPerWarp;
   static constexpr int kBiasFloats = 6144;       // every layer's padded bias + the final dot weights, when they fit
   static constexpr int kBarOff = kBiasOff + kBiasFloats * 4;
@@ -186,6 +186,15 @@ __device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, in
     }
   }
 }
+// Arrival for data whose bulk stores have already completed (relaxed increment, see p2_arrive).
+__device__ __forceinline__ void p2_arrive_done(const Pass2Params& p, int dep_kind, int rb, int lane) {
+  if (lane == 0) {
+    int* ctr = p.ready + dep_kind * p.rb_cap + rb;
+    if (p.n_static == p.n_total) { red_relaxed_gpu_add(ctr, 1); return; }
+    const int old = atom_relaxed_gpu_add(ctr, 1);
+    if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+  }
+}
 // A producer thread waits until block rb of buffer dep_kind is complete (static items only).  The data is read by
 // TMA only (async proxy, from L2): the proxy fence orders the counter read before the bulk loads that follow.
 __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, int rb) {
@@ -199,22 +208,119 @@ __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, 
   fence_proxy_async_all();
 }
 
-// Tail-embedding pieces of one 64-column chunk for this warp's 32 rows: coalesced 16-byte loads (two rows per
-// instruction) into the warp's staging tile, row r at r * 256 B, piece t at t ^ (r & 7).
-__device__ __forceinline__ void p2_stage_tail(uint8_t* st, unsigned long long trow_bits, int col0, int n_valid, int lane) {
-  float4 tv[16];
+// Tail-embedding values of 32 columns for this warp's 32 rows: coalesced 16-byte loads (four rows per instruction),
+// then into the warp's 4 KB staging tile (row r at r * 128 B, piece t at t ^ (r & 7)) for row-per-lane reads.
+__device__ __forceinline__ void p2_tail_load(float4 (&tv)[8], unsigned long long trow_bits, int col0, int n_valid, int lane) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = i * 2 + (lane >> 4), t = lane & 15;
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), t = lane & 7;
     const float* tp2 = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, trow_bits, r));
     tv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tp2 != nullptr && col0 + t * 4 < n_valid) tv[i] = ld_stream4(tp2 + col0 + t * 4);
   }
+}
+__device__ __forceinline__ void p2_tail_stage(uint8_t* st, const float4 (&tv)[8], int lane) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int r = i * 2 + (lane >> 4), t = lane & 15;
-    *reinterpret_cast<float4*>(st + r * 256 + ((t ^ (r & 7)) << 4)) = tv[i];
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), t = lane & 7;
+    *reinterpret_cast<float4*>(st + r * 128 + ((t ^ (r & 7)) << 4)) = tv[i];
   }
+  __syncwarp();
+}
+// this lane's row against 32 generator outputs f[0..31] (columns col0 .. col0 + 31)
+__device__ __forceinline__ void p2_tail_dot(const uint8_t* st, const float* f, int col0, int n_valid, int lane, float& d, float& pp,
+                                            float& tt) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const float4 x = *reinterpret_cast<const float4*>(st + lane * 128 + ((t ^ (lane & 7)) << 4));
+    if (col0 + t * 4 < n_valid) {
+      d += f[4 * t] * x.x + f[4 * t + 1] * x.y + f[4 * t + 2] * x.z + f[4 * t + 3] * x.w;
+      pp += f[4 * t] * f[4 * t] + f[4 * t + 1] * f[4 * t + 1] + f[4 * t + 2] * f[4 * t + 2] + f[4 * t + 3] * f[4 * t + 3];
+      tt += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+  }
+  __syncwarp();
+}
+
+// Gather group for the common layout (E = 128, Z <= 128, unpadded xg / xd rows): four rows through the warp's staging
+// tile and out with bulk stores, so that the arrival can follow cp.async.bulk.wait_group (a few hundred clocks)
+// instead of a release fence over 28 generic stores per lane.  Returns after the stores have completed.
+__device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long long group, int lane, uint8_t* st) {
+  const long long r0 = group * 4;
+  __nv_bfloat16* xg = static_cast<__nv_bfloat16*>(g.xg);
+  __nv_bfloat16* xd = static_cast<__nv_bfloat16*>(g.xd);
+  const float* src = nullptr;
+  bool bad = false;
+  if (lane < 12) {   // lane l resolves the source row of (row l / 3, operand l % 3): 0 head, 1 relation, 2 tail
+    const long long row = r0 + lane / 3;
+    const int which = lane % 3;
+    if (row < g.B) {
+      if (which == 0) {
+        if (g.heads) { long long i = g.heads[row * g.head_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        else src = g.h + row * g.E;
+      } else if (which == 1) {
+        if (g.rels) { long long i = g.rels[row * g.rel_stride]; if (i < 0 || i >= g.R) { bad = true; i = 0; } src = g.rel_emb + i * g.E; }
+        else src = g.r + row * g.E;
+      } else if (xd != nullptr) {
+        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        else src = g.t + row * g.E;
+      }
+    }
+  }
+  if (bad) atomicOr(g.err_flag, 1);
+  const unsigned long long sp = reinterpret_cast<unsigned long long>(src);
+  const int Z4 = g.Z >> 2;
+  const int wg = 2 * g.E + g.Z, wd = 3 * g.E;            // row widths (elements) = ldg / ldd on this path
+  float4 hv[4], rv[4], tv[4], zv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float* ph = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, sp, j * 3 + 0));
+    const float* pr = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, sp, j * 3 + 1));
+    const float* pt = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, sp, j * 3 + 2));
+    const long long row = r0 + j;
+    hv[j] = rv[j] = tv[j] = zv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < g.B) {
+      hv[j] = ld_stream4(ph + 4 * lane);
+      rv[j] = ld_stream4(pr + 4 * lane);
+      if (xd != nullptr) tv[j] = ld_stream4(pt + 4 * lane);
+      if (xg != nullptr && lane < Z4) zv[j] = ld_stream4(g.z + row * g.Z + 4 * lane);
+    }
+  }
+  const long long nrow = min(4ll, g.B - r0);   // rows of a group are consecutive in xg / xd: one bulk store each
+  // the staging tile holds one of the two outputs at a time (4 x 640 B, then 4 x 768 B)
+  if (xg != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(st) + j * wg;
+      store4<__nv_bfloat16>(o + 4 * lane, hv[j]);
+      store4<__nv_bfloat16>(o + g.E + 4 * lane, rv[j]);
+      if (lane < Z4) store4<__nv_bfloat16>(o + 2 * g.E + 4 * lane, zv[j]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && nrow > 0) {
+      bulk_store_1d(xg + r0 * wg, st, static_cast<uint32_t>(nrow * wg * 2));
+      tma_store_commit();
+      if (xd != nullptr) tma_store_wait_read<0>();
+    }
+    __syncwarp();
+  }
+  if (xd != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(st) + j * wd;
+      store4<__nv_bfloat16>(o + 4 * lane, hv[j]);
+      store4<__nv_bfloat16>(o + g.E + 4 * lane, rv[j]);
+      store4<__nv_bfloat16>(o + 2 * g.E + 4 * lane, tv[j]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && nrow > 0) {
+      bulk_store_1d(xd + r0 * wd, st, static_cast<uint32_t>(nrow * wd * 2));
+      tma_store_commit();
+    }
+  }
+  if (lane == 0) tma_store_wait<0>();
   __syncwarp();
 }
 
@@ -243,6 +349,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   uint2* ring = reinterpret_cast<uint2*>(bias_bar + 1);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + kP2Ring);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  volatile long long* t_issue = reinterpret_cast<volatile long long*>(smem + L::kXchgOff + L::kXchgBytes);  // [kP2Stages], diagnostics
   float* xchg = reinterpret_cast<float*>(smem + L::kXchgOff);
   float* sbias = reinterpret_cast<float*>(smem + L::kBiasOff);
 
@@ -327,7 +434,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           const int i = ticket - p.seg[sg].start;
           const int nt = p.seg[sg].n_tiles;
           it = make_uint2(static_cast<uint32_t>(p.seg[sg].kind) | (static_cast<uint32_t>(i % nt) << 8) | kItemPoll,
-                          static_cast<uint32_t>(i / nt));
+                          static_cast<uint32_t>(p.seg[sg].rb0 + i / nt));
         } else if (ticket < p.n_total) {
           const long long t = tr ? clock64() : 0;
           unsigned long long d;
@@ -399,6 +506,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             p2_poll_dep(p, ly.dep_kind, rb);
             if (tr) { w_dep += clock64() - t; if (ti) ti[1] = clock64(); } }
           for (int kb = 0; kb < npre; ++kb) {
+            if (tr) t_issue[stage] = clock64();
             tma_load_2d_pair(smem + stage * L::kStage, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
             if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
           }
@@ -412,6 +520,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStage;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
+          if (tr) t_issue[stage] = clock64();
           tma_load_2d_pair(sa + L::kA, &p.tm_w[kind], lead_full + stage * 8, kb * kBlockK, w_row);
           tma_load_2d_pair(sa, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
           if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
@@ -424,7 +533,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     // ------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
-      long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0;
+      long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0, lat_sum = 0, lat_n = 0, lat_max = 0;
       for (;;) {
         if (tr) { const long long t = clock64(); mbar_wait(&sched_full[slot], sphase); w_item += clock64() - t; }
         else mbar_wait(&sched_full[slot], sphase);
@@ -441,8 +550,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < ly.num_kb; ++kb) {
-          if (tr) { const long long t = clock64(); mbar_wait(&full_bar[stage], phase); w_full += clock64() - t; ++n_kb; }
-          else mbar_wait(&full_bar[stage], phase);
+          if (tr) {
+            const long long t = clock64(); mbar_wait(&full_bar[stage], phase); const long long t1 = clock64();
+            w_full += t1 - t; ++n_kb;
+            const long long lat = t1 - t_issue[stage];
+            if (t1 - t > 64) { lat_sum += lat; lat_n += 1; if (lat > lat_max) lat_max = lat; }  // only when the MMA really waited
+          } else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStage);
           const uint64_t da = make_kmajor_sw128_desc(sa);
@@ -455,7 +568,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         umma_commit_pair(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; tr[15] = w_item; }
+      if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; tr[15] = w_item; tr[237] = lat_sum; tr[238] = lat_n; tr[239] = lat_max; }
     }
     __syncwarp();
   } else {
@@ -464,7 +577,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int half = wep >> 2;         // which half of a tile's 64-column chunks this warp takes
     uint8_t* st = smem + L::kStagingOff + wep * L::kStagingPerWarp;
-    uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0, buf = 0;
+    uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     int pend_kind = -1, pend_rb = 0;   // previous tile's block: announced once its bulk stores have completed
@@ -473,7 +586,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     // the block's counter) where this warp would otherwise idle -- while its next TMEM load is in flight, or before
     // it blocks on the ring / an accumulator that is not ready yet.  It is never postponed past a point where the
     // warp can block indefinitely: the item it would wait for may depend on exactly this arrival.
-    mbar_wait(bias_bar, 0);  // biases have landed (issued in the prologue)
+    bool bias_ok = false;
     long long pf_delay = 0, pf_wait = 0, pf_total = 0, pf_n = 0, t_pend = 0;
     auto flush_pend = [&]() {
       if (pend_kind >= 0) {
@@ -513,11 +626,18 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       }
       if (group >= 0) {
         flush_pend();
-        pass_gather_group<FASTG ? 1 : 2>(p.gather, group, lane);
-        if (tr && threadIdx.x == 64) tr[250] = clock64();
-        p2_arrive(p, DEP_X, g_rb, lane, false);
+        if (FASTG) {
+          p2_gather_group_bulk(p.gather, group, lane, st);   // returns with the rows in global memory
+          if (tr && threadIdx.x == 64) tr[250] = clock64();
+          p2_arrive_done(p, DEP_X, g_rb, lane);
+        } else {
+          pass_gather_group<2>(p.gather, group, lane);
+          if (tr && threadIdx.x == 64) tr[250] = clock64();
+          p2_arrive(p, DEP_X, g_rb, lane, false);
+        }
         continue;
       }
+      if (!bias_ok) { mbar_wait(bias_bar, 0); bias_ok = true; }  // the bulk copies issued in the prologue have landed
       const int n_blk = (it.x >> 8) & 0xff;
       const int rb = static_cast<int>(it.y);
       long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
@@ -530,13 +650,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
 
       // PEPI_TANH prefetch (before the accumulator wait, i.e. behind the tile's MMA time): tail index, then the tail
-      // row pieces of this warp's first chunk, coalesced, into the staging tile
+      // values of this warp's first chunk -- columns 0..31 into the staging tile, columns 32..63 kept in registers
       const bool want_cos = ly.epi == PEPI_TANH && p.cosine != nullptr;
       unsigned long long trow_bits = 0ull;
+      float4 tv2[8];
       if (want_cos) {
-        // the staging tile may still be the source of an activation store issued by an earlier tile of this warp
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
+        flush_pend();  // the staging tile may still be the source of an activation store of an earlier tile
         const float* trow = nullptr;
         if (row_ok) {
           long long tid = p.tail_idx[grow * p.tail_stride];
@@ -544,7 +663,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           trow = p.tail_tab + tid * p.n_valid;
         }
         trow_bits = reinterpret_cast<unsigned long long>(trow);
-        if (half < n_chunks) p2_stage_tail(st, trow_bits, n0 + half * 64, p.n_valid, lane);
+        if (half < n_chunks) {
+          float4 tv1[8];
+          p2_tail_load(tv1, trow_bits, n0 + half * 64, p.n_valid, lane);
+          p2_tail_load(tv2, trow_bits, n0 + half * 64 + 32, p.n_valid, lane);
+          p2_tail_stage(st, tv1, lane);
+        }
       }
       {
         const long long t = (tr && lane == 0) ? clock64() : 0;
@@ -570,11 +694,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         for (int c = half; c < n_chunks; c += 2) {
           if (tp) tq0 = clock64();
           const float4* b4 = reinterpret_cast<const float4*>(bias_tile + c * 64);
-          // this staging buffer is free once the bulk store issued two chunks ago has read it
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
           if (tp) tq1 = clock64();
-          uint8_t* sbuf = st + buf * 4096;
+          uint8_t* sbuf = st;
           tmem_ld_wait();
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, vb);
           if (tp) tq2 = clock64();
@@ -582,16 +703,20 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             float4 bq[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) bq[t] = b4[t];
+            uint4 w[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float4 ba = bq[2 * t], bb = bq[2 * t + 1];
-              uint4 w;
-              w.x = bias_leaky_pack(va[8 * t + 0], va[8 * t + 1], ba.x, ba.y, slope);
-              w.y = bias_leaky_pack(va[8 * t + 2], va[8 * t + 3], ba.z, ba.w, slope);
-              w.z = bias_leaky_pack(va[8 * t + 4], va[8 * t + 5], bb.x, bb.y, slope);
-              w.w = bias_leaky_pack(va[8 * t + 6], va[8 * t + 7], bb.z, bb.w, slope);
-              *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w;
+              w[t].x = bias_leaky_pack(va[8 * t + 0], va[8 * t + 1], ba.x, ba.y, slope);
+              w[t].y = bias_leaky_pack(va[8 * t + 2], va[8 * t + 3], ba.z, ba.w, slope);
+              w[t].z = bias_leaky_pack(va[8 * t + 4], va[8 * t + 5], bb.x, bb.y, slope);
+              w[t].w = bias_leaky_pack(va[8 * t + 6], va[8 * t + 7], bb.z, bb.w, slope);
             }
+            // the staging tile is free once the previous chunk's bulk store has read it (hidden behind the math above)
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w[t];
           }
           float4 bq[8];
 #pragma unroll
@@ -623,7 +748,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
             tma_store_commit();
           }
-          buf ^= 1;
           if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; ph_m1 += tq5 - tq2; ph_w2 += tq6 - tq5; }
         }
         if (half >= n_chunks) {  // narrow tile: this warp had no chunk, still has to release the accumulator
@@ -701,7 +825,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         float* part = p.part_g + (static_cast<size_t>(rb) * p.slots_g) * 3 * kP2Rows;
         for (int c = half; c < n_chunks; c += 2) {
           const int col0 = n0 + c * 64;
-          if (want_cos && c != half) p2_stage_tail(st, trow_bits, col0, p.n_valid, lane);  // later chunks of a wide tile
+          if (want_cos && c != half) {  // later chunks of a wide tile: fetch their tail values now
+            float4 tv1[8];
+            p2_tail_load(tv1, trow_bits, col0, p.n_valid, lane);
+            p2_tail_load(tv2, trow_bits, col0 + 32, p.n_valid, lane);
+            p2_tail_stage(st, tv1, lane);
+          }
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
@@ -724,20 +853,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           }
           if (tpt) tr[234] = clock64();
           if (want_cos) {
-            // tail pieces are in the staging tile: one row per lane
+            // columns 0..31 are in the staging tile (one row per lane); then columns 32..63 take their place
             float cs_dot = 0.f, cs_pp = 0.f, cs_tt = 0.f;
-            if (col0 < p.n_valid) {
-#pragma unroll
-              for (int t = 0; t < 16; ++t) {
-                const float4 x = *reinterpret_cast<const float4*>(st + lane * 256 + ((t ^ (lane & 7)) << 4));
-                if (col0 + t * 4 < p.n_valid) {
-                  cs_dot += f[4 * t] * x.x + f[4 * t + 1] * x.y + f[4 * t + 2] * x.z + f[4 * t + 3] * x.w;
-                  cs_pp += f[4 * t] * f[4 * t] + f[4 * t + 1] * f[4 * t + 1] + f[4 * t + 2] * f[4 * t + 2] + f[4 * t + 3] * f[4 * t + 3];
-                  cs_tt += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-                }
-              }
-            }
-            __syncwarp();
+            p2_tail_dot(st, f, col0, p.n_valid, lane, cs_dot, cs_pp, cs_tt);
+            p2_tail_stage(st, tv2, lane);
+            p2_tail_dot(st, f + 32, col0 + 32, p.n_valid, lane, cs_dot, cs_pp, cs_tt);
             if (in_cta) {
               // the two warps of this lane quarter hold the row's two halves: the upper one hands its sums over
               // through shared memory, the lower one finishes (fixed order: columns 0..63 + columns 64..127)

@@ -537,17 +537,24 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   if (nrb <= p.p0_blocks) {
     // small batch: every item is a static ticket, layer by layer (a topological order); the producers poll the
     // dependency counters and nothing is pushed
-    static const char* order_env = getenv("PBG_SEG_ORDER");
-    int order[5] = {IT_G_L0, IT_D_L0, IT_G_L1, IT_D_L1, IT_G_L2};
-    if (order_env && strlen(order_env) == 5)
-      for (int i = 0; i < 5; ++i) order[i] = order_env[i] - '0';
+    // Waves: the row blocks are cut into `waves` groups and the layer phases of the groups are interleaved
+    // (L0 of every wave, then L1 of every wave, then L2), so that a pair waiting for one wave's hand-off has another
+    // wave's tiles next in its ticket sequence.
+    static const int waves_env = [] { const char* e = getenv("PBG_WAVES"); return e ? atoi(e) : 1; }();
+    const int waves = std::max(1, std::min(waves_env, std::min(nrb, 3)));
+    static const int phase_kinds[3][2] = {{IT_G_L0, IT_D_L0}, {IT_G_L1, IT_D_L1}, {IT_G_L2, -1}};
     int start = 0;
-    for (int i = 0; i < 5; ++i) {
-      const int k = order[i];
-      if (k < 0 || k > 4 || !on[k]) continue;
-      const int cnt = nrb * p.layer[k].n_tiles;
-      p.seg[p.n_seg++] = P2Segment{k, p.layer[k].n_tiles, start, cnt};
-      start += cnt;
+    for (int ph = 0; ph < 3; ++ph) {
+      for (int wv = 0; wv < waves; ++wv) {
+        const int rb_lo = static_cast<int>(static_cast<long long>(nrb) * wv / waves);
+        const int rb_hi = static_cast<int>(static_cast<long long>(nrb) * (wv + 1) / waves);
+        for (int j = 0; j < 2; ++j) {
+          const int k = phase_kinds[ph][j];
+          if (k < 0 || !on[k] || rb_hi == rb_lo) continue;
+          p.seg[p.n_seg++] = P2Segment{k, p.layer[k].n_tiles, start, rb_lo};
+          start += (rb_hi - rb_lo) * p.layer[k].n_tiles;
+        }
+      }
     }
     p.n_static = start;
     if (start != total) return fail(c, PBG_ERR_INVALID, "internal: static item list does not cover the pass");
@@ -576,7 +583,8 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.trace = c->trace;
   // programmatic dependent launch: this pass may begin its prologue while the previous kernel of the stream drains
   static const bool pdl = [] { const char* e = getenv("PBG_PDL"); return !e || atoi(e) != 0; }();
-  const bool fastg = c->dims.embed_dim == 128 && c->dims.noise_dim % 4 == 0 && c->dims.noise_dim <= 128;
+  const bool fastg = c->dims.embed_dim == 128 && c->dims.noise_dim % 4 == 0 && c->dims.noise_dim <= 128 &&
+                     c->kg0p == c->kg0 && c->kd0p == c->kd0;  // the bulk-store gather writes unpadded rows
   cudaError_t le;
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
     if (p.trace) le = fastg ? launch_p2<true, true>(c, p, grid, a.stream, pdl) : launch_p2<true, false>(c, p, grid, a.stream, pdl);

@@ -59,6 +59,8 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     P(f"   per CTA: items {hdr[:, 12].mean():.1f}  k-blocks {hdr[:, 9].mean():.1f} (max {hdr[:, 9].max():.0f})  -> MMA floor {hdr[:, 9].mean() * 512:.0f} clk")
     P(f"   producer: dep wait {hdr[:, 11].mean():.0f} (max {hdr[:, 11].max():.0f})  empty wait {hdr[:, 1].mean():.0f}")
     P(f"   mma: full wait {hdr[:, 3].mean():.0f} (max {hdr[:, 3].max():.0f})  tmem wait {hdr[:, 4].mean():.0f}")
+    ln = t[:, 238].sum().clamp_min(1)
+    P(f"   leader's loads that the MMA waited for: {int(t[:, 238].sum())} of {int(hdr[:, 9].sum())} k-blocks, issue -> both CTAs' data landed: mean {t[:, 237].sum() / ln:.0f} clk, max {t[:, 239].max():.0f}")
     P(f"   epilogue warp 2: acc wait {hdr[:, 7].mean():.0f}  busy {hdr[:, 10].mean():.0f}")
     ph = t[:, 240:256]
     nchunk = ph[:, 3].clamp_min(1); ntile = ph[:, 5].clamp_min(1)
