@@ -14,10 +14,17 @@ per step, batch-index sharded (weak scaling: 4096 x N triplets per step), output
 with an all-gather over NVLink at N > 1.  E = 128, Z = 64, H = 1024, 65536 entities, 64 relations, random-init
 weights with the frozen seeds of pbg/synth.py.
 
+Lanes: one 4096-triplet pass is a chain of dependent layers (gather -> L0 -> L1 -> L2) that cannot keep 148 SMs busy
+for its whole duration, so the steps -- independent requests -- are issued round-robin on `--lanes` streams, each
+with its own engine (ctx) whose passes occupy `--ctas` SMs; passes of different lanes run side by side.
+`--lanes 1` is the single-stream, full-width configuration.
+
 Printed JSON (one line, rank 0):
   value      samples/s, whole job, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
-  e2e        same metric through the C-ABI host entry point pbg_score_triplets_host: per step H2D of the
-             triplets + latents from pinned host memory and D2H of predictions / scores / logits / probs
+  e2e        same metric through the C-ABI host entry point pbg_score_triplets_host (synchronous), one host thread
+             per lane: per step H2D of the triplets + latents from pinned host memory and D2H of the result the
+             reference's score_triplets returns (generator scores, discriminator logits and probabilities,
+             pro_b_gan_infer.py:204-209)
   roofline   dominant kernel vs the measured bf16 tensor peak (MEASURED_PEAKS.json)
   cpu_baseline  the CPU oracle (oracle/prot_b_gan_oracle.py, a port: the reference ships no model) on the
              box's host cores, bounded sample
@@ -163,13 +170,22 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     B = args.batch
     Bg = B * world
     K, W = args.steps, args.warmup
+    # Lanes: a 4096-triplet pass is a chain of dependent layers and cannot keep 148 SMs busy for its whole duration,
+    # so independent steps run side by side -- one engine (ctx) + stream per lane, each pass on `ctas` SMs.
+    S = max(1, args.lanes)
+    num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    # default width: a third of the device per pass (more lanes than that keep a queue of CTAs behind every SM)
+    ctas = args.ctas if args.ctas > 0 else (0 if S == 1 else max(2, (num_sms // min(S, 3)) // 2 * 2))
     G, D = synth.make_models(m.ModularGenerator, m.ModularDiscriminator)
-    eng = m.make_fused_engine(G.to(dev), D.to(dev))
+    G, D = G.to(dev), D.to(dev)
+    engines = [m.make_fused_engine(G, D, ctas=ctas) for _ in range(S)]
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
     node_emb, rel_w = (t.to(dev) for t in synth.make_tables(NUM_ENTITIES, NUM_RELATIONS, E))
 
     # ---- input pool: distinct pre-staged batches whose footprint exceeds L2, visited round-robin
     per_batch = B * (3 * 8 + Z * 4 + E * 2 + 3 * 4)
     P = max(8, math.ceil(1.6 * L2_BYTES / per_batch))
+    P = (P + S - 1) // S * S          # pool entry i always runs on lane i % S
     lo, hi = shard.shard_bounds(Bg, world, rank)
     pool = []
     for i in range(P):
@@ -181,95 +197,140 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                "probs": torch.empty(B, dtype=torch.float32, device=dev)}
         pool.append((trip, z, out))
     if world > 1:
-        full_gen = torch.empty(Bg, E, dtype=torch.bfloat16, device=dev)
-        full_small = torch.empty(world, 3, B, dtype=torch.float32, device=dev)
-        small = torch.empty(3, B, dtype=torch.float32, device=dev)
+        full_gen = [torch.empty(Bg, E, dtype=torch.bfloat16, device=dev) for _ in range(S)]
+        full_small = [torch.empty(world, 3, B, dtype=torch.float32, device=dev) for _ in range(S)]
+        small = [torch.empty(3, B, dtype=torch.float32, device=dev) for _ in range(S)]
 
     def compute(i: int):
+        """One pass, issued on the current stream."""
         trip, z, out = pool[i % P]
-        eng.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
-                           precision="bf16", out_dtype=torch.bfloat16, out=out)
+        engines[i % S].score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True,
+                                      want_disc=True, precision="bf16", out_dtype=torch.bfloat16, out=out)
         return out
 
     def step(i: int):
-        out = compute(i)
-        if world > 1:  # reassemble the outputs on every rank (north_star: NVLink all-gather)
-            dist.all_gather_into_tensor(full_gen, out["gen_out"])
-            small[0].copy_(out["gen_scores"]); small[1].copy_(out["logits"]); small[2].copy_(out["probs"])
-            dist.all_gather_into_tensor(full_small, small)
+        lane = i % S
+        with torch.cuda.stream(streams[lane]):
+            out = compute(i)
+            if world > 1:  # reassemble the outputs on every rank (north_star: NVLink all-gather)
+                dist.all_gather_into_tensor(full_gen[lane], out["gen_out"])
+                small[lane][0].copy_(out["gen_scores"]); small[lane][1].copy_(out["logits"]); small[lane][2].copy_(out["probs"])
+                dist.all_gather_into_tensor(full_small[lane], small[lane])
 
-    # ---- optional CUDA graphs (single GPU): one graph per pool entry, replayed round-robin
+    # ---- optional CUDA graphs (single GPU): one graph per pool entry, captured and replayed on its lane's stream
     use_graphs = args.graphs and world == 1
     graphs = []
-    compute(0); eng.check_indices()
-    l0 = eng.launch_count
-    compute(0)
-    launches_per_step = eng.launch_count - l0
+    for lane in range(S):
+        with torch.cuda.stream(streams[lane]):
+            compute(lane)
+    torch.cuda.synchronize()
+    for e in engines:
+        e.check_indices()
+    l0 = engines[0].launch_count
+    with torch.cuda.stream(streams[0]):
+        compute(0)
+    torch.cuda.synchronize()
+    launches_per_step = engines[0].launch_count - l0
     if use_graphs:
-        side = torch.cuda.Stream(dev)
-        with torch.cuda.stream(side):
-            for i in range(P):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
+        for i in range(P):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(streams[i % S]):
+                with torch.cuda.graph(g, stream=streams[i % S]):
                     compute(i)
-                graphs.append(g)
+            graphs.append(g)
         torch.cuda.synchronize()
 
         def step(i: int):  # noqa: F811
-            graphs[i % P].replay()
+            with torch.cuda.stream(streams[i % S]):
+                graphs[i % P].replay()
 
+    main = torch.cuda.current_stream(dev)
+
+    def fork():
+        e = torch.cuda.Event(); e.record(main)
+        for s in streams:
+            s.wait_event(e)
+
+    def join():
+        for s in streams:
+            e = torch.cuda.Event(); e.record(s); main.wait_event(e)
+
+    fork()
     for i in range(W):
         step(i)
+    join()
     torch.cuda.synchronize(); barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         torch.cuda.synchronize(); barrier()
-        ev0.record()
+        ev0.record(main)
+        fork()
         for i in range(K):
             step(W + i)
-        ev1.record()
+        join()
+        ev1.record(main)
         torch.cuda.synchronize(); barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
-    eng.check_indices()
+    for e in engines:
+        e.check_indices()
     value = Bg * K / (ms * 1e-3)
     gpu_launches = launches_per_step * K
 
-    # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+    # ---- e2e: host buffers through the C-ABI host entry point (synchronous: H2D, pass, D2H, one sync per call);
+    #      one host thread per lane keeps `S` calls in flight, each on its own ctx, like a multi-threaded server
+    import threading
     hp = []
-    for i in range(min(P, 16)):
+    for i in range(min(P, 16 * S)):
         trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=9000 + i)[lo:hi].contiguous().pin_memory()
         z = synth.make_latents(Bg, Z, seed=9500 + i)[lo:hi].contiguous().pin_memory()
         hp.append((trip, z))
-    h_gen = torch.empty(B, E).pin_memory(); h_sc = torch.empty(B).pin_memory()
-    h_lg = torch.empty(B).pin_memory(); h_pb = torch.empty(B).pin_memory()
+    h_out = [(None, torch.empty(B).pin_memory(), torch.empty(B).pin_memory(), torch.empty(B).pin_memory())
+             for _ in range(S)]  # score_triplets returns scores / logits / probabilities, not the predicted embeddings
     Ke = min(K, 2000)
 
-    def e2e_step(i: int):
-        trip, z = hp[i % len(hp)]
-        eng.score_triplets_host(node_emb, rel_w, trip, z, h_gen, h_sc, h_lg, h_pb, precision="bf16")
+    def e2e_worker(lane: int, first: int, last: int):
+        torch.cuda.set_device(local_rank)
+        h_gen, h_sc, h_lg, h_pb = h_out[lane]
+        for i in range(first + lane, last, S):
+            trip, z = hp[i % len(hp)]
+            engines[lane].score_triplets_host(node_emb, rel_w, trip, z, h_gen, h_sc, h_lg, h_pb, precision="bf16")
 
-    for i in range(max(3, min(W, 10))):
-        e2e_step(i)
+    def e2e_run(first: int, last: int):
+        ts = [threading.Thread(target=e2e_worker, args=(lane, first, last)) for lane in range(S)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    e2e_run(0, max(3 * S, min(W, 10)))
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
-    for i in range(Ke):
-        e2e_step(i)  # synchronous: returns after the D2H of this step's results
+    e2e_run(0, Ke)  # every call returns after the D2H of its results
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e = {"value": Bg * Ke / e2e_s, "unit": "samples/s",
-           "h2d_bytes_per_step": B * (3 * 8 + Z * 4) * world, "d2h_bytes_per_step": B * (E * 4 + 3 * 4) * world,
-           "steps": Ke, "api": "pbg_score_triplets_host (C ABI, pinned host buffers, one sync per step)"}
+           "h2d_bytes_per_step": B * (3 * 8 + Z * 4) * world, "d2h_bytes_per_step": B * 3 * 4 * world,
+           "steps": Ke, "api": f"pbg_score_triplets_host (C ABI, pinned host buffers, one sync per call), "
+                               f"{S} host thread(s), one ctx each"}
 
-    # ---- roofline of the dominant kernel: per-kernel CUDA events on the launch stream, same workload
+    # ---- roofline of the dominant kernel: per-kernel CUDA events on its launch stream, the same lanes in flight
     peaks = measured_peaks()
-    prof_steps = min(K, 200)
-    eng.profile_enable(True)
-    eng.profile_read()
+    prof_steps = min(K, 60 * S)
+    for e in engines:
+        e.profile_enable(True); e.profile_read()
+    fork()
     for i in range(prof_steps):
-        compute(i)
-    prof = eng.profile_read()
-    eng.profile_enable(False)
+        with torch.cuda.stream(streams[i % S]):
+            compute(i)
+    join()
+    torch.cuda.synchronize()
+    prof = {}
+    for e in engines:
+        for k, v in e.profile_read().items():
+            a = prof.setdefault(k, [0.0, 0])
+            a[0] += v[0]; a[1] += v[1]
+        e.profile_enable(False)
     flops = {"g_l0": 2 * B * (2 * E + Z) * H, "g_l1": 2 * B * H * H, "g_l2": 2 * B * H * E,
              "d_l0": 2 * B * 3 * E * H, "d_l1": 2 * B * H * (H // 2) + 2 * B * (H // 2)}
     flops["pass"] = B * FLOP_SAMPLE  # the fused kernel runs the whole G + D pass
@@ -278,13 +339,18 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     ach = flops[dom] / (kinds[dom]["ms_per_launch"] * 1e-3) / 1e12
     step_tflops = FLOP_SAMPLE * value / world / 1e12
     peak = peaks["bf16_burst"]  # timed regions here last well under a second: burst figure
+    share = (ctas if ctas > 0 else num_sms) / num_sms
     traffic = None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         traffic = json.loads(tf.read_text()).get(dom)
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": traffic, "peak_source": peaks["source"] + ", burst figure",
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
+                "frac": step_tflops / peak, "traffic": traffic, "peak_source": peaks["source"] + ", burst figure",
+                "note": f"achieved = algorithmic flops of the {S} launches in flight / average launch duration x "
+                        f"overlap, taken as flops per sample x measured throughput of the timed region; one launch "
+                        f"alone: see per_launch (it occupies {ctas if ctas > 0 else num_sms} of {num_sms} SMs)",
                 "flops_per_launch": flops[dom], "us_per_launch": kinds[dom]["ms_per_launch"] * 1e3,
+                "per_launch": {"achieved": ach, "sm_share": share, "peak_share": peak * share, "frac_of_share": ach / (peak * share)},
                 "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak,
                                "frac_of_sustained": step_tflops / peaks["bf16_sustained"],
                                "flops_per_sample": FLOP_SAMPLE},
@@ -304,6 +370,7 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
             "config": {"workload": workload_name(B, world), "global_batch": Bg, "parallelism": f"dp{world}",
                        "l2": f"inputs rotate over {P} distinct pre-staged batches ({P * per_batch / 2**20:.0f} MiB "
                              f"> 126 MiB L2); no flush", "cuda_graphs": bool(use_graphs),
+                       "lanes": S, "ctas_per_pass": ctas if ctas > 0 else num_sms,
                        "collective": "all-gather of outputs (NCCL)" if world > 1 else "none"},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "cpu_baseline": cpu,
@@ -322,6 +389,8 @@ def main() -> None:
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=4096, help="triplets per GPU per step")
     ap.add_argument("--graphs", type=int, default=1)
+    ap.add_argument("--lanes", type=int, default=6, help="independent passes in flight (one ctx + stream each)")
+    ap.add_argument("--ctas", type=int, default=0, help="SMs per pass (0: all SMs / lanes, in whole CTA pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

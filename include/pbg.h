@@ -170,6 +170,13 @@ int pbg_profile_read(pbg_ctx* ctx, double* ms, int64_t* count);
  * then enables / disables tracing and zeroes the buffer. */
 int pbg_debug_trace(pbg_ctx* ctx, int enable, int64_t* host_out, int64_t n_slots);
 
+/* Launch width of the fused pass kernel: how many CTAs (= SMs; rounded down to whole CTA pairs, at least 2) one
+ * pass occupies.  0 (the default) = every SM of the device.  A 4096-triplet pass is a chain of dependent layers
+ * and does not fill 148 SMs for its whole duration, so a server that has independent passes in flight gives each
+ * its own ctx and stream and a width of about a third of the device: the passes then run side by side
+ * (bench.py does exactly that).  One pass alone is fastest at full width. */
+int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

@@ -102,6 +102,7 @@ struct pbg_ctx {
   EncodeTiledFn encode = nullptr;
   std::map<std::tuple<long long, int, int>, ItemList> item_cache;  // (rows, run_g, run_d) -> work-item order
   long long launches = 0;
+  int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
   bool profiling = false;
   long long* trace = nullptr;  // device, 16 slots x num_sms (pbg_debug_trace)
   struct ProfRec { cudaEvent_t a, b; int kind; };
@@ -293,7 +294,8 @@ struct LayerPlan { int num_kb, bn, n_tiles; };
 // CTAs per launch of the pass kernel: one per SM unless PBG_GRID asks for fewer (several streams sharing the GPU)
 int pass_grid(const pbg_ctx* c) {
   static const int env = [] { const char* e = getenv("PBG_GRID"); return e ? atoi(e) : 0; }();
-  return (env > 0 && env < c->num_sms) ? env : c->num_sms;
+  const int want = c->launch_ctas > 0 ? c->launch_ctas : env;
+  return (want > 0 && want < c->num_sms) ? std::max(2, want) : c->num_sms;
 }
 
 int build_items(pbg_ctx* c, long long rows, bool run_g, bool run_d, ItemList** out) {
@@ -532,7 +534,10 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
   // phase 0: the first row blocks are gathered by the epilogue warps of all CTAs before the roles start (one 4-row
   // group per warp); the rest of the batch goes through gather items (64 rows each)
-  p.p0_blocks = std::min(nrb, std::max(1, grid * kEpiWarps / kP2GroupsPerBlock));
+  // Batches up to PBG_STATIC_MAX_RB row blocks run entirely from the static ticket list (phase 0 gathers every row,
+  // in as many rounds per warp as it takes); larger ones gather one round in phase 0 and push the rest.
+  static const int static_max_rb = [] { const char* e = getenv("PBG_STATIC_MAX_RB"); return e ? atoi(e) : 256; }();
+  p.p0_blocks = nrb <= static_max_rb ? nrb : std::min(nrb, std::max(1, grid * kEpiWarps / kP2GroupsPerBlock));
   p.phase0_groups = p.p0_blocks * kP2GroupsPerBlock;
   if (nrb <= p.p0_blocks) {
     // small batch: every item is a static ticket, layer by layer (a topological order); the producers poll the
@@ -627,6 +632,14 @@ int pbg_abi_version(void) { return PBG_ABI_VERSION; }
 const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pbg_set_launch_width(pbg_ctx* c, int n_ctas) {
+  if (!c) return PBG_ERR_INVALID;
+  if (n_ctas < 0) return fail(c, PBG_ERR_INVALID, "launch width must be >= 0");
+  c->launch_ctas = n_ctas;
+  c->item_cache.clear();  // the single-CTA kernel's cached tiling plans depend on the grid
+  return PBG_OK;
+}
 
 int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
   if (!out || !dims) return fail(nullptr, PBG_ERR_INVALID, "null argument");

@@ -138,13 +138,14 @@ class ModularDiscriminator(_CudaModule):
         return res["logits"], res["probs"]
 
 
-def make_fused_engine(generator: ModularGenerator, discriminator: ModularDiscriminator) -> Engine:
+def make_fused_engine(generator: ModularGenerator, discriminator: ModularDiscriminator, ctas: int = 0) -> Engine:
     """One ctx holding both models: the G + D pass of ProtBGANInference.score_triplets
-    (pro_b_gan_infer.py:186-209) as a single call sharing one gather."""
+    (pro_b_gan_infer.py:186-209) as a single call sharing one gather.  `ctas`: SMs per pass (0 = all); servers
+    with several independent passes in flight use one engine + stream per lane at about a third of the device."""
     generator._require_inference()
     discriminator._require_inference()
     eng = Engine(generator.embed_dim, generator.noise_dim, generator.hidden_dim, discriminator.hidden_dim,
-                 generator._device(), LEAKY_SLOPE)
+                 generator._device(), LEAKY_SLOPE, ctas)
     eng.load_generator(generator.folded_layers())
     eng.load_discriminator(discriminator.folded_layers())
     return eng

@@ -22,6 +22,7 @@ SYMBOLS = (
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
+    "pbg_set_launch_width",
 )
 
 
@@ -70,6 +71,7 @@ def load() -> C.CDLL:
         "pbg_debug_trace": (C.c_int, [vp, i32, vp, i64]),
         "pbg_check_indices": (C.c_int, [vp, vp]),
         "pbg_launch_count": (i64, [vp]),
+        "pbg_set_launch_width": (C.c_int, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -52,7 +52,7 @@ class Engine:
     """Owns a pbg_ctx.  Methods take / return CUDA tensors on the engine's device."""
 
     def __init__(self, embed_dim: int, noise_dim: int, g_hidden: int, d_hidden: int,
-                 device: torch.device | str | int, leaky_slope: float = 0.2):
+                 device: torch.device | str | int, leaky_slope: float = 0.2, ctas: int = 0):
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError(f"pro-b-gan_b200 runs only on CUDA (sm_100a) devices, got {device}; there is no CPU fallback")
@@ -68,6 +68,12 @@ class Engine:
             self._h = C.c_void_p(0)
             cabi.check(st, None)
         self.g_loaded = self.d_loaded = False
+        if ctas:
+            self.set_launch_width(ctas)
+
+    def set_launch_width(self, ctas: int) -> None:
+        """CTAs (SMs) one fused pass occupies; 0 = the whole device.  See include/pbg.h."""
+        cabi.check(self._lib.pbg_set_launch_width(self._h, int(ctas)), self._h)
 
     def __del__(self):
         h = getattr(self, "_h", None)

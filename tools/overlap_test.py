@@ -19,7 +19,7 @@ for i in range(P):
     out = {"gen_out": torch.empty(B, 128, dtype=torch.bfloat16, device=dev), "gen_scores": torch.empty(B, device=dev),
            "logits": torch.empty(B, device=dev), "probs": torch.empty(B, device=dev)}
     pool.append((trip, z, out))
-for S in (1, 2, 3, 4):
+for S in [int(x) for x in (sys.argv[2:] or ['1', '2', '3', '4'])]:
     engines = [m.make_fused_engine(G, D) for _ in range(S)]
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
 
