@@ -112,6 +112,7 @@ def run_reference(args, rank: int, world: int) -> None:
     shipped, so the oracle port is what runs (kind = "port").  Rank 0 only."""
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every core
     fn, cores = cpu_oracle_pass_factory(args.batch)
     t0 = time.perf_counter(); fn(); t_one = time.perf_counter() - t0
     # bound the whole run to ~2 minutes: shrink the per-step sample if K full batches would take longer
@@ -187,38 +188,70 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
     P = max(8, math.ceil(1.6 * L2_BYTES / per_batch))
     P = (P + S - 1) // S * S          # pool entry i always runs on lane i % S
     lo, hi = shard.shard_bounds(Bg, world, rank)
-    pool = []
+    # one contiguous result block per pool entry and rank: [gen_out bf16 B x E | scores | logits | probs fp32 B each].
+    # N > 1: the blocks of all ranks for one step form that step's assembled output [world, block] on EVERY rank.
+    #   exchange "p2p"  (default): the buffers live in symmetric memory and every pass writes its rows straight into
+    #                   the peers' copies from the kernel epilogues (result mirrors, NVLink stores; no collective)
+    #   exchange "nccl": one all-gather of the block per step on a per-lane communicator
+    blk_bytes = B * (2 * E + 12)
+    exchange = "none"
+    peer_ptrs = None
+    if world > 1:
+        exchange = args.exchange
+        if exchange == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                sym = symm_mem.empty(P * world * blk_bytes, dtype=torch.uint8, device=dev)
+                hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
+                peer_ptrs = [int(x) for x in hdl.buffer_ptrs]
+            except Exception as ex:  # symmetric memory unavailable on this box: fall back to the collective
+                if rank == 0:
+                    print(f"bench.py: symmetric memory unavailable ({ex}); using the NCCL all-gather", file=sys.stderr)
+                exchange = "nccl"
+        # every rank must take the same path
+        flag = torch.tensor([1 if exchange == "p2p" else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange, peer_ptrs = "nccl", None
+    if exchange != "p2p":
+        sym = torch.empty(P * max(world, 1) * blk_bytes, dtype=torch.uint8, device=dev)
+    pool, mirrors = [], []
     for i in range(P):
         trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=4321 + i)[lo:hi].contiguous().to(dev)
         z = synth.make_latents(Bg, Z, seed=1234 + i)[lo:hi].contiguous().to(dev)
-        out = {"gen_out": torch.empty(B, E, dtype=torch.bfloat16, device=dev),
-               "gen_scores": torch.empty(B, dtype=torch.float32, device=dev),
-               "logits": torch.empty(B, dtype=torch.float32, device=dev),
-               "probs": torch.empty(B, dtype=torch.float32, device=dev)}
+        off = (i * world + rank) * blk_bytes
+        blk = sym[off:off + blk_bytes]
+        f32 = blk[B * 2 * E:].view(torch.float32)
+        out = {"gen_out": blk[:B * 2 * E].view(torch.bfloat16).view(B, E),
+               "gen_scores": f32[0:B], "logits": f32[B:2 * B], "probs": f32[2 * B:3 * B], "block": blk,
+               "assembled": sym[i * world * blk_bytes:(i + 1) * world * blk_bytes]}
         pool.append((trip, z, out))
-    if world > 1:
-        full_gen = [torch.empty(Bg, E, dtype=torch.bfloat16, device=dev) for _ in range(S)]
-        full_small = [torch.empty(world, 3, B, dtype=torch.float32, device=dev) for _ in range(S)]
-        small = [torch.empty(3, B, dtype=torch.float32, device=dev) for _ in range(S)]
+        if exchange == "p2p":
+            base = [peer_ptrs[r] + off for r in range(world) if r != rank]
+            mirrors.append({"gen_out": base, "gen_scores": [b + B * 2 * E for b in base],
+                            "logits": [b + B * 2 * E + 4 * B for b in base], "probs": [b + B * 2 * E + 8 * B for b in base]})
+    if exchange == "nccl":
+        # one communicator per lane: collectives of different lanes run on different streams, and NCCL requires the
+        # collectives of ONE communicator to execute in the same order on every rank
+        lane_pg = [dist.new_group(ranks=list(range(world)), backend="nccl") for _ in range(S)]
 
     def compute(i: int):
         """One pass, issued on the current stream."""
         trip, z, out = pool[i % P]
+        if exchange == "p2p":
+            engines[i % S].set_result_mirrors(**mirrors[i % P])
         engines[i % S].score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True,
                                       want_disc=True, precision="bf16", out_dtype=torch.bfloat16, out=out)
+        if exchange == "nccl":  # reassemble the outputs on every rank (north_star: NVLink all-gather)
+            dist.all_gather_into_tensor(out["assembled"], out["block"], group=lane_pg[i % S])
         return out
 
     def step(i: int):
-        lane = i % S
-        with torch.cuda.stream(streams[lane]):
-            out = compute(i)
-            if world > 1:  # reassemble the outputs on every rank (north_star: NVLink all-gather)
-                dist.all_gather_into_tensor(full_gen[lane], out["gen_out"])
-                small[lane][0].copy_(out["gen_scores"]); small[lane][1].copy_(out["logits"]); small[lane][2].copy_(out["probs"])
-                dist.all_gather_into_tensor(full_small[lane], small[lane])
+        with torch.cuda.stream(streams[i % S]):
+            compute(i)
 
-    # ---- optional CUDA graphs (single GPU): one graph per pool entry, captured and replayed on its lane's stream
-    use_graphs = args.graphs and world == 1
+    # ---- optional CUDA graphs: one graph per pool entry (pass + all-gather), captured and replayed on its lane's stream
+    use_graphs = bool(args.graphs) and exchange != "nccl"   # NCCL inside per-lane graphs hung on this box: eager there
     graphs = []
     for lane in range(S):
         with torch.cuda.stream(streams[lane]):
@@ -371,7 +404,9 @@ def run_b200(args, rank: int, local_rank: int, world: int) -> None:
                        "l2": f"inputs rotate over {P} distinct pre-staged batches ({P * per_batch / 2**20:.0f} MiB "
                              f"> 126 MiB L2); no flush", "cuda_graphs": bool(use_graphs),
                        "lanes": S, "ctas_per_pass": ctas if ctas > 0 else num_sms,
-                       "collective": "all-gather of outputs (NCCL)" if world > 1 else "none"},
+                       "collective": {"none": "none", "p2p": "none: every pass writes its result rows into all peers' symmetric-memory "
+                                      "windows from its epilogues (NVLink stores)", "nccl": "all-gather of outputs (NCCL, "
+                                      "one per step)"}[exchange]},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "cpu_baseline": cpu,
         }
@@ -390,6 +425,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=4096, help="triplets per GPU per step")
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=6, help="independent passes in flight (one ctx + stream each)")
+    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p", help="N > 1: how the outputs are re-assembled")
     ap.add_argument("--ctas", type=int, default=0, help="SMs per pass (0: all SMs / lanes, in whole CTA pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

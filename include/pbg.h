@@ -177,6 +177,17 @@ int pbg_debug_trace(pbg_ctx* ctx, int enable, int64_t* host_out, int64_t n_slots
  * (bench.py does exactly that).  One pass alone is fastest at full width. */
 int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
 
+/* Result mirrors -- the output exchange of a batch-sharded multi-GPU job without a collective.  After this call every
+ * bf16-mode pass of the ctx writes each result row not only to the caller's own gen_out / gen_scores / logits /
+ * probs but also, at the same row index, to the n (<= 7) mirror buffers given here: device pointers into peer GPUs'
+ * memory (peer access enabled: CUDA IPC, cuMem fabric handles, torch symmetric memory ...), already offset to the
+ * caller's shard.  The stores travel over NVLink from the last layers' epilogues; they are complete when the pass
+ * has completed on its stream, so readers on other GPUs need their usual cross-rank synchronisation (a barrier, a
+ * flag) and nothing else.  An array may be NULL when the matching result is not requested; n = 0 clears.
+ * Passes that cannot honour mirrors (fp32 mode, models too wide for the pair kernel) fail with PBG_ERR_UNSUPPORTED. */
+int pbg_set_result_mirrors(pbg_ctx* ctx, int n, void* const* gen_out, float* const* gen_scores,
+                           float* const* logits, float* const* probs);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

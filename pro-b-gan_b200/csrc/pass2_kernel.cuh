@@ -41,6 +41,7 @@ constexpr int kP2Rows = 256;                        // rows of one pair tile = o
 constexpr int kP2GroupsPerBlock = kP2Rows / 4;      // 4-row gather groups per block
 constexpr int kP2GatherPerBlock = 4;                // gather items per block: 64 rows = 16 warps x 4 rows
 constexpr int kP2WarpsPerPair = 2 * kEpiWarps;
+constexpr int kMaxMirrors = 7;                      // peers of an 8-GPU box
 
 struct P2Layer {
   int num_kb;        // K / 64
@@ -90,8 +91,13 @@ struct alignas(64) Pass2Params {
   int w3_off;           // offset (floats) of w3 in the shared-memory copy, or -1
   float* part_d;        // [nrb][slots_d][256]
   int slots_d;
+  // result mirrors: the same rows of every result are also written to these buffers (peer GPUs' windows over NVLink:
+  // the output all-gather of a batch-sharded job without a collective; pbg_set_result_mirrors)
+  int n_mirror;
+  void* mir_gen[kMaxMirrors]; float* mir_cos[kMaxMirrors]; float* mir_logits[kMaxMirrors]; float* mir_probs[kMaxMirrors];
   long long* trace;
 };
+static_assert(sizeof(Pass2Params) <= 4096, "kernel parameter space");
 
 struct P2Smem {
   static constexpr int kA = 128 * kBlockK * 2;
@@ -811,8 +817,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             const long long gr = static_cast<long long>(rb) * kP2Rows + j * 32 + lane;
             if (gr < p.M) {
               const float logit = s[j] + p.b3;
+              const float prob = 1.f / (1.f + __expf(-logit));
               p.logits[gr] = logit;
-              if (p.probs != nullptr) p.probs[gr] = 1.f / (1.f + __expf(-logit));
+              if (p.probs != nullptr) p.probs[gr] = prob;
+              for (int mi = 0; mi < p.n_mirror; ++mi) {
+                p.mir_logits[mi][gr] = logit;
+                if (p.mir_probs[mi] != nullptr) p.mir_probs[mi][gr] = prob;
+              }
             }
           }
         }
@@ -867,7 +878,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
               if (half == 0) {
                 const float d = cs_dot + xq[0], pp = cs_pp + xq[1], tt = cs_tt + xq[2];
                 // F.cosine_similarity(pred, t, dim=1), eps = 1e-8 on each norm (pro_b_gan_infer.py:202)
-                if (row_ok) p.cosine[grow] = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+                if (row_ok) {
+                  const float cs = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+                  p.cosine[grow] = cs;
+                  for (int mi = 0; mi < p.n_mirror; ++mi) p.mir_cos[mi][grow] = cs;
+                }
               }
               asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the slot may be rewritten after this
             } else if (col0 < p.n_valid) {
@@ -880,22 +895,25 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           if (tpt) tr[235] = clock64();
           if (want_out && row_ok) {
             // one row per lane, 16-byte stores (2 MB for a 4096-row pass: not worth a transpose through shared memory)
-            if (p.out_f32) {
-              float* orow = static_cast<float*>(p.gen_out) + grow * p.ld_gen + col0;
+            for (int mi = -1; mi < p.n_mirror; ++mi) {   // -1: the caller's own buffer, then the mirrors
+              void* base = mi < 0 ? p.gen_out : p.mir_gen[mi];
+              if (p.out_f32) {
+                float* orow = static_cast<float*>(base) + grow * p.ld_gen + col0;
 #pragma unroll
-              for (int t = 0; t < 16; ++t)
-                if (col0 + t * 4 < p.n_valid)
-                  *reinterpret_cast<float4*>(orow + t * 4) = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
-            } else {
-              __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.gen_out) + grow * p.ld_gen + col0;
+                for (int t = 0; t < 16; ++t)
+                  if (col0 + t * 4 < p.n_valid)
+                    *reinterpret_cast<float4*>(orow + t * 4) = make_float4(f[4 * t], f[4 * t + 1], f[4 * t + 2], f[4 * t + 3]);
+              } else {
+                __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(base) + grow * p.ld_gen + col0;
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                uint4 w;
-                w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
-                w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
-                w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
-                w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
-                if (col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(orow + t * 8) = w;
+                for (int t = 0; t < 8; ++t) {
+                  uint4 w;
+                  w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
+                  w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
+                  w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
+                  w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
+                  if (col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(orow + t * 8) = w;
+                }
               }
             }
           }
@@ -919,7 +937,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 pp += __ldcg(part + (k * 3 + 1) * kP2Rows + r);
                 tt += __ldcg(part + (k * 3 + 2) * kP2Rows + r);
               }
-              if (gr < p.M) p.cosine[gr] = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+              if (gr < p.M) {
+                const float cs = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
+                p.cosine[gr] = cs;
+                for (int mi = 0; mi < p.n_mirror; ++mi) p.mir_cos[mi][gr] = cs;
+              }
             }
           }
         }

@@ -103,6 +103,8 @@ struct pbg_ctx {
   std::map<std::tuple<long long, int, int>, ItemList> item_cache;  // (rows, run_g, run_d) -> work-item order
   long long launches = 0;
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
+  int n_mirror = 0;     // pbg_set_result_mirrors
+  void* mir_gen[kMaxMirrors] = {}; float* mir_cos[kMaxMirrors] = {}; float* mir_logits[kMaxMirrors] = {}; float* mir_probs[kMaxMirrors] = {};
   bool profiling = false;
   long long* trace = nullptr;  // device, 16 slots x num_sms (pbg_debug_trace)
   struct ProfRec { cudaEvent_t a, b; int kind; };
@@ -368,6 +370,7 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   gp.xd = a.run_d ? w.xd0 : nullptr; gp.ldd = bf ? c->kd0p : c->kd0;
   gp.B = rows; gp.err_flag = c->err_flag;
   const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
+  if (!bf && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors are a bf16-mode feature");
   if (!bf) {  // the bf16 mode gathers inside the fused pass kernel
     LaunchScope ls(c, PBG_K_GATHER, s);
     gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp);
@@ -385,6 +388,7 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
     if (a.run_g) bias_floats += c->g[0].np + c->g[1].np + c->g[2].np;
     if (a.run_d) bias_floats += c->d[0].np + 2 * c->d[1].np;
     const bool use_v1 = force_v1 || bias_floats > P2Smem::kBiasFloats;
+    if (use_v1 && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors need the pair kernel (model too wide)");
     return use_v1 ? launch_pass(c, w, a, gp, off, rows, gen_out, scores)
                   : launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
   } else {
@@ -586,6 +590,17 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.probs = a.probs ? a.probs + off : nullptr;
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
+  p.n_mirror = c->n_mirror;
+  for (int i = 0; i < c->n_mirror; ++i) {
+    if (gen_out && !c->mir_gen[i]) return fail(c, PBG_ERR_INVALID, "result mirror %d has no gen_out buffer", i);
+    if (scores && !c->mir_cos[i]) return fail(c, PBG_ERR_INVALID, "result mirror %d has no gen_scores buffer", i);
+    if (a.logits && !c->mir_logits[i]) return fail(c, PBG_ERR_INVALID, "result mirror %d has no logits buffer", i);
+    const size_t es = a.out_dtype == PBG_DT_BF16 ? 2 : 4;
+    p.mir_gen[i] = c->mir_gen[i] ? static_cast<char*>(c->mir_gen[i]) + static_cast<size_t>(off) * c->dims.embed_dim * es : nullptr;
+    p.mir_cos[i] = c->mir_cos[i] ? c->mir_cos[i] + off : nullptr;
+    p.mir_logits[i] = c->mir_logits[i] ? c->mir_logits[i] + off : nullptr;
+    p.mir_probs[i] = (c->mir_probs[i] && a.probs) ? c->mir_probs[i] + off : nullptr;
+  }
   // programmatic dependent launch: this pass may begin its prologue while the previous kernel of the stream drains
   static const bool pdl = [] { const char* e = getenv("PBG_PDL"); return !e || atoi(e) != 0; }();
   const bool fastg = c->dims.embed_dim == 128 && c->dims.noise_dim % 4 == 0 && c->dims.noise_dim <= 128 &&
@@ -632,6 +647,20 @@ int pbg_abi_version(void) { return PBG_ABI_VERSION; }
 const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pbg_set_result_mirrors(pbg_ctx* c, int n, void* const* gen_out, float* const* gen_scores, float* const* logits,
+                           float* const* probs) {
+  if (!c) return PBG_ERR_INVALID;
+  if (n < 0 || n > kMaxMirrors) return fail(c, PBG_ERR_INVALID, "at most %d result mirrors", kMaxMirrors);
+  c->n_mirror = n;
+  for (int i = 0; i < kMaxMirrors; ++i) {
+    c->mir_gen[i] = (i < n && gen_out) ? gen_out[i] : nullptr;
+    c->mir_cos[i] = (i < n && gen_scores) ? gen_scores[i] : nullptr;
+    c->mir_logits[i] = (i < n && logits) ? logits[i] : nullptr;
+    c->mir_probs[i] = (i < n && probs) ? probs[i] : nullptr;
+  }
+  return PBG_OK;
+}
 
 int pbg_set_launch_width(pbg_ctx* c, int n_ctas) {
   if (!c) return PBG_ERR_INVALID;

@@ -22,7 +22,7 @@ SYMBOLS = (
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
-    "pbg_set_launch_width",
+    "pbg_set_launch_width", "pbg_set_result_mirrors",
 )
 
 
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
         "pbg_check_indices": (C.c_int, [vp, vp]),
         "pbg_launch_count": (i64, [vp]),
         "pbg_set_launch_width": (C.c_int, [vp, i32]),
+        "pbg_set_result_mirrors": (C.c_int, [vp, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

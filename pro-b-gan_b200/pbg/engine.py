@@ -75,6 +75,20 @@ class Engine:
         """CTAs (SMs) one fused pass occupies; 0 = the whole device.  See include/pbg.h."""
         cabi.check(self._lib.pbg_set_launch_width(self._h, int(ctas)), self._h)
 
+    def set_result_mirrors(self, gen_out=(), gen_scores=(), logits=(), probs=()) -> None:
+        """Device addresses (ints) of up to 7 mirror buffers per result, e.g. peer GPUs' windows: every bf16-mode
+        pass also writes its rows there (include/pbg.h: pbg_set_result_mirrors).  Empty lists clear."""
+        n = max(len(gen_out), len(gen_scores), len(logits), len(probs))
+        def arr(ptrs):
+            if not ptrs:
+                return None
+            if len(ptrs) != n:
+                raise ValueError("every given mirror list must have the same length")
+            return (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in ptrs])
+        a = [arr(gen_out), arr(gen_scores), arr(logits), arr(probs)]
+        cabi.check(self._lib.pbg_set_result_mirrors(self._h, n, *[C.cast(x, C.c_void_p) if x is not None else None for x in a]),
+                   self._h)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:
