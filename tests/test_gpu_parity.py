@@ -311,3 +311,65 @@ def test_batch_larger_than_one_chunk(engine, dev_tables, synth, dev):
     tail = engine.score_triplets(node_emb, rel_w, trip[65536:], z[65536:], want_gen_out=True, want_disc=True,
                                  precision="bf16")
     assert torch.equal(full["gen_out"][65536:], tail["gen_out"]) and torch.equal(full["logits"][65536:], tail["logits"])
+
+
+# ----------------------------------------------------------------------------- launch width, lanes, result mirrors
+def _pass(eng, dev_tables, trip, z, out=None):
+    return eng.score_triplets(*dev_tables, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
+                              precision="bf16", out_dtype=torch.bfloat16, out=out)
+
+
+@pytest.mark.parametrize("B", [300, 4096, 9000])
+def test_launch_width_does_not_change_a_single_bit(cuda_models, engine, dev_tables, synth, dev, B):
+    """pbg_set_launch_width: the pass on 2, 48 or all SMs gives identical results (fixed-order reductions)."""
+    import modular_prot_b_gan as m
+    trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
+    ref = {k: v.clone() for k, v in _pass(engine, dev_tables, trip, z).items()}
+    for ctas in (2, 48, 74):
+        eng = m.make_fused_engine(*cuda_models, ctas=ctas)
+        res = _pass(eng, dev_tables, trip, z)
+        eng.check_indices()
+        for k in ref:
+            assert torch.equal(res[k], ref[k]), f"width {ctas}: {k} differs"
+
+
+def test_passes_on_concurrent_lanes_match_sequential(cuda_models, dev_tables, synth, dev):
+    """Three ctxs on three streams, 48 SMs each, passes in flight together (bench.py's lanes)."""
+    import modular_prot_b_gan as m
+    B, S, R = 4096, 3, 4
+    engines = [m.make_fused_engine(*cuda_models, ctas=48) for _ in range(S)]
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    inputs = [(synth.make_triplets(B, seed=100 + i).to(dev), synth.make_latents(B, seed=200 + i).to(dev)) for i in range(S * R)]
+    ref = [{k: v.clone() for k, v in _pass(engines[0], dev_tables, t, z).items()} for t, z in inputs]
+    torch.cuda.synchronize()
+    got = []
+    for i, (t, z) in enumerate(inputs):
+        with torch.cuda.stream(streams[i % S]):
+            got.append(_pass(engines[i % S], dev_tables, t, z))
+    torch.cuda.synchronize()
+    for e in engines:
+        e.check_indices()
+    for i in range(len(inputs)):
+        for k in ref[i]:
+            assert torch.equal(got[i][k], ref[i][k]), f"step {i}: {k} differs"
+
+
+def test_result_mirrors_receive_the_same_rows(cuda_models, dev_tables, synth, dev):
+    """pbg_set_result_mirrors with two mirror buffers (same device here; peers' windows in a multi-GPU job)."""
+    import modular_prot_b_gan as m
+    B, E = 1000, 128
+    eng = m.make_fused_engine(*cuda_models)
+    trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
+    mir = [{"gen_out": torch.zeros(B, E, dtype=torch.bfloat16, device=dev), "gen_scores": torch.zeros(B, device=dev),
+            "logits": torch.zeros(B, device=dev), "probs": torch.zeros(B, device=dev)} for _ in range(2)]
+    eng.set_result_mirrors(**{k: [d[k].data_ptr() for d in mir] for k in mir[0]})
+    res = _pass(eng, dev_tables, trip, z)
+    torch.cuda.synchronize()
+    for d in mir:
+        for k in d:
+            assert torch.equal(d[k], res[k]), f"mirror {k} differs"
+    with pytest.raises(Exception):   # mirrors are a bf16-mode feature: the fp32 path must refuse, not ignore them
+        eng.score_triplets(*dev_tables, trip, z, want_gen_out=True, precision="fp32")
+    eng.set_result_mirrors()
+    res2 = _pass(eng, dev_tables, trip, z)
+    assert torch.equal(res2["logits"], res["logits"])
