@@ -895,7 +895,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           if (tpt) tr[235] = clock64();
           if (want_out && row_ok) {
             // one row per lane, 16-byte stores (2 MB for a 4096-row pass: not worth a transpose through shared memory)
-            for (int mi = -1; mi < p.n_mirror; ++mi) {   // -1: the caller's own buffer, then the mirrors
+            // the caller's own buffer: 16-byte stores straight from registers; mirrors (peer GPUs over NVLink): the row
+            // segment goes through this lane's 128 bytes of the staging tile and out as one 128-byte bulk store per
+            // mirror -- 16-byte stores would cross NVLink as 16-byte packets
+            const bool bulk_mirror = p.n_mirror > 0 && (p.n_valid & 63) == 0;
+            for (int mi = -1; mi < (bulk_mirror ? 0 : p.n_mirror); ++mi) {
               void* base = mi < 0 ? p.gen_out : p.mir_gen[mi];
               if (p.out_f32) {
                 float* orow = static_cast<float*>(base) + grow * p.ld_gen + col0;
@@ -916,6 +920,38 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 }
               }
             }
+            if (bulk_mirror) {
+              uint8_t* myrow = st + lane * 128;   // only this lane writes and (through its bulk stores) reads it
+              const int rounds = p.out_f32 ? 2 : 1;
+              for (int rd = 0; rd < rounds; ++rd) {
+                tma_store_wait_read<0>();         // this lane's earlier bulk stores have read the row
+                if (p.out_f32) {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t)
+                    *reinterpret_cast<float4*>(myrow + t * 16) =
+                        make_float4(f[32 * rd + 4 * t], f[32 * rd + 4 * t + 1], f[32 * rd + 4 * t + 2], f[32 * rd + 4 * t + 3]);
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) {
+                    uint4 w;
+                    w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
+                    w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
+                    w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
+                    w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
+                    *reinterpret_cast<uint4*>(myrow + t * 16) = w;
+                  }
+                }
+                fence_proxy_async_smem();
+                const size_t es = p.out_f32 ? 4 : 2;
+                const size_t byte_off = (static_cast<size_t>(grow) * p.ld_gen + col0) * es + static_cast<size_t>(rd) * 128;
+                for (int mi = 0; mi < p.n_mirror; ++mi) bulk_store_1d(static_cast<char*>(p.mir_gen[mi]) + byte_off, myrow, 128);
+                tma_store_commit();
+              }
+            }
+          }
+          if (want_out && p.n_mirror > 0) {   // (warp-uniform) the staging tile is free again when every lane's stores have read it
+            tma_store_wait_read<0>();
+            __syncwarp();
           }
         }
         if (half >= n_chunks) {
@@ -950,7 +986,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (ti) ti[3] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) tma_store_wait<0>();  // nothing of this warp's staging may be in flight when the CTA exits
+    tma_store_wait<0>();  // nothing of this warp's staging (any lane's bulk stores) may be in flight when the CTA exits
     if (tr && threadIdx.x == 64) {
       tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
       tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
