@@ -3,9 +3,9 @@
 //   gather/concat -> G.L0 -> G.L1 -> G.L2 (tanh, cosine)         (pro_b_gan_infer.py:186-188, :201-202)
 //                 -> D.L0 -> D.L1 (+ final H/2 -> 1 dot, sigmoid) (pro_b_gan_infer.py:207, :302)
 //
-// Same data flow as pass_kernel.cuh (work items through a ready queue in global memory, activations handed from
-// layer to layer through L2, per-row-block arrival counters), re-cut for the L2 -> SM operand bandwidth that bounds
-// it: two CTAs on one TPC form a pair and compute one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2
+// Activations are handed from layer to layer through L2 (bf16, row-major) with per-row-block arrival counters in
+// global memory: no grid-wide barrier, no launch per layer.  The tiling is cut for the L2 -> SM operand bandwidth
+// that bounds the main loop: two CTAs on one TPC form a pair and compute one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2
 // (M = 256: 128 rows of A per CTA; the BLOCK_N rows of W are split in halves, one per CTA), so a 64-deep k-block
 // costs each SM 16 KB of A + 16 KB of W (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for a single-CTA
 // 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).
@@ -18,10 +18,11 @@
 //                                                                      CTAs' rings
 //   warps 2..9  epilogue of its 128 rows / gather items       warps 2..9  epilogue of its 128 rows / gather items
 //
-// Tickets below n_static index a static, topologically ordered item list described by a few segments (small
-// batches: every item; the producers poll the item's dependency counter, after prefetching its W tiles, instead of
-// being pushed); tickets above it index the ready queue (large batches: an item is pushed when its inputs are
-// complete).  Either way a pair works through its tickets in order, which makes any topological order deadlock-free.
+// Tickets index a static, topologically ordered item list described by a few segments in the kernel parameters
+// (layer by layer, row-block major).  A pair takes its tickets in order from one atomic counter and works through
+// them in order, which makes any topological order deadlock-free (the unfinished item with the smallest ticket never
+// waits on anything unfinished); the producers poll an item's dependency counter after prefetching its W tiles.
+// The gather of every row is "phase 0" of the epilogue warps.
 //
 // Epilogues: bias + LeakyReLU -> bf16 -> swizzled staging (double-buffered per warp) -> TMA store; the final
 // discriminator dot and the cosine against the tail embedding are written as per-64-column partials that the last
@@ -66,18 +67,14 @@ struct alignas(64) Pass2Params {
   GatherParams gather;
   unsigned layer_mask;
   int poll_ns;
-  int phase0_groups;    // 4-row gather groups done by the epilogue warps of all CTAs before the roles start
-  int p0_blocks;        // = phase0_groups / 64
-  int gather_ahead;     // gather items run this many row blocks ahead of the first-layer tiles
-  int n_total;          // items this launch pops in total (static + pushed)
-  int n_static;         // tickets served from the segment table; pushes are disabled when n_static == n_total
+  int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
+  int n_total;          // tickets of this launch
   int n_seg;
   P2Segment seg[16];
   int nrb;              // 256-row blocks in this pass
   int rb_cap;           // stride of the counter arrays
   int M;                // rows in this pass
   float slope;
-  unsigned long long* queue;
   PassSched* sched;
   int* ready;           // [DEP_KINDS][rb_cap]
   int* fin;             // [FIN_KINDS][rb_cap]
@@ -143,28 +140,6 @@ __device__ __forceinline__ int p2_dep_target(const Pass2Params& p, int dep_kind)
   const int producer = dep_kind == DEP_G0 ? IT_G_L0 : (dep_kind == DEP_D0 ? IT_D_L0 : IT_G_L1);
   return p.layer[producer].n_tiles * kP2WarpsPerPair;
 }
-__device__ __forceinline__ void p2_push_gather(const Pass2Params& p, int rb) {
-  const int base = atomicAdd(&p.sched->q_tail, kP2GatherPerBlock);
-  for (int u = 0; u < kP2GatherPerBlock; ++u) st_relaxed_gpu_u64(p.queue + base + u, pass_item(IT_GATHER, u, rb));
-}
-// One thread, after its arrival completed block rb of buffer dep_kind: push the block's consumers.  One fence orders
-// everything the producers wrote (acquired through the counter) before the relaxed queue stores that follow it.
-__device__ __noinline__ void p2_group_done(const Pass2Params& p, int dep_kind, int rb) {
-  fence_acq_rel_gpu();
-  if (dep_kind == DEP_X) {
-    const int ng = (p.layer_mask & (1u << IT_G_L0)) ? p.layer[IT_G_L0].n_tiles : 0;
-    const int nd = (p.layer_mask & (1u << IT_D_L0)) ? p.layer[IT_D_L0].n_tiles : 0;
-    const int base = atomicAdd(&p.sched->q_tail, ng + nd);
-    for (int n = 0; n < ng; ++n) st_relaxed_gpu_u64(p.queue + base + n, pass_item(IT_G_L0, n, rb));
-    for (int n = 0; n < nd; ++n) st_relaxed_gpu_u64(p.queue + base + ng + n, pass_item(IT_D_L0, n, rb));
-    if (rb >= p.p0_blocks && rb + p.gather_ahead < p.nrb) p2_push_gather(p, rb + p.gather_ahead);
-  } else {
-    const int kind = dep_kind == DEP_G0 ? IT_G_L1 : (dep_kind == DEP_D0 ? IT_D_L1 : IT_G_L2);
-    const int nt = p.layer[kind].n_tiles;
-    const int base = atomicAdd(&p.sched->q_tail, nt);
-    for (int n = 0; n < nt; ++n) st_relaxed_gpu_u64(p.queue + base + n, pass_item(kind, n, rb));
-  }
-}
 // A warp announces "my part of block rb of buffer dep_kind is in global memory".
 //   generic stores (gather): the warp barrier orders every lane's stores before lane 0's release increment.
 //   bulk stores (activations): lane 0 issued them; cp.async.bulk.wait_group 0 returns once they have been performed
@@ -176,32 +151,21 @@ __device__ __forceinline__ void p2_arrive(const Pass2Params& p, int dep_kind, in
   __syncwarp();
   if (lane == 0) {
     int* ctr = p.ready + dep_kind * p.rb_cap + rb;
-    const bool pushing = p.n_static != p.n_total;
     if (async_stores) {
       const long long t0 = t_wait ? clock64() : 0;
       tma_store_wait<0>();
       if (t_wait) *t_wait += clock64() - t0;
-      if (!pushing) { red_relaxed_gpu_add(ctr, 1); return; }
-      const int old = atom_relaxed_gpu_add(ctr, 1);
-      if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
-    } else if (!pushing) {
-      red_release_gpu_add(ctr, 1);  // consumers poll: nobody needs to know who was last
+      red_relaxed_gpu_add(ctr, 1);
     } else {
-      const int old = atom_release_gpu_add(ctr, 1);
-      if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
+      red_release_gpu_add(ctr, 1);
     }
   }
 }
 // Arrival for data whose bulk stores have already completed (relaxed increment, see p2_arrive).
 __device__ __forceinline__ void p2_arrive_done(const Pass2Params& p, int dep_kind, int rb, int lane) {
-  if (lane == 0) {
-    int* ctr = p.ready + dep_kind * p.rb_cap + rb;
-    if (p.n_static == p.n_total) { red_relaxed_gpu_add(ctr, 1); return; }
-    const int old = atom_relaxed_gpu_add(ctr, 1);
-    if (old + 1 == p2_dep_target(p, dep_kind)) p2_group_done(p, dep_kind, rb);
-  }
+  if (lane == 0) red_relaxed_gpu_add(p.ready + dep_kind * p.rb_cap + rb, 1);
 }
-// A producer thread waits until block rb of buffer dep_kind is complete (static items only).  The data is read by
+// A producer thread waits until block rb of buffer dep_kind is complete.  The data is read by
 // TMA only (async proxy, from L2): the proxy fence orders the counter read before the bulk loads that follow.
 __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, int rb) {
   const int target = p2_dep_target(p, dep_kind);
@@ -331,8 +295,6 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-constexpr uint32_t kItemPoll = 1u << 16;   // ring item flag: the producers poll the dependency counter themselves
-
 // Always 0 (an item's bits 24..31 are never set), but only known at run time: added to the address of a consumer's
 // sched_empty arrive so that the arrive cannot be issued before the load of the ring slot has returned.
 __device__ __forceinline__ uint32_t ring_dep(uint2 it) { return (it.x >> 24) << 3; }
@@ -419,38 +381,21 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);    // the leader's, as seen from either CTA
   const uint32_t sched_empty_addr = mapa_u32(smem_u32(sched_empty), 1);  // the scheduler CTA's
   const uint32_t ring_addr = mapa_u32(smem_u32(ring), 1);
-  const bool pushing = p.n_static != p.n_total;
-
-  // ---- queue seeding: gather items of the first row blocks past phase 0
-  if (pushing && blockIdx.x == 0 && threadIdx.x == 0) {
-    for (int rb = p.p0_blocks; rb < min(p.nrb, p.p0_blocks + p.gather_ahead); ++rb) p2_push_gather(p, rb);
-  }
   if (warp == 1 && !leader) {
     // ------------------------------------------------------------ scheduler (one thread of the peer CTA)
     if (lane == 0) {
       uint32_t slot = 0, sphase = 0;
-      long long w_dep = 0;
       const uint32_t lead_sched_full = mapa_u32(smem_u32(sched_full), 0);
       for (;;) {
         const int ticket = atomicAdd(&p.sched->q_head, 1);
         uint2 it = make_uint2(IT_END, 0u);
-        if (ticket < p.n_static) {
+        if (ticket < p.n_total) {
           int sg = 0;
           while (sg + 1 < p.n_seg && ticket >= p.seg[sg + 1].start) ++sg;
           const int i = ticket - p.seg[sg].start;
           const int nt = p.seg[sg].n_tiles;
-          it = make_uint2(static_cast<uint32_t>(p.seg[sg].kind) | (static_cast<uint32_t>(i % nt) << 8) | kItemPoll,
+          it = make_uint2(static_cast<uint32_t>(p.seg[sg].kind) | (static_cast<uint32_t>(i % nt) << 8),
                           static_cast<uint32_t>(p.seg[sg].rb0 + i / nt));
-        } else if (ticket < p.n_total) {
-          const long long t = tr ? clock64() : 0;
-          unsigned long long d;
-          uint32_t spins = 0;
-          while ((d = ld_relaxed_gpu_u64(p.queue + (ticket - p.n_static))) == 0ull) {
-            __nanosleep(p.poll_ns);
-            if (++spins > 4000000u) pbg_wait_timed_out("ready-queue (ticket, total)", ticket, p.n_total);
-          }
-          if (tr) w_dep += clock64() - t;
-          it = make_uint2((static_cast<uint32_t>(d) & 0xff) - 1u | (static_cast<uint32_t>(d) & 0xff00u), static_cast<uint32_t>(d >> 32));
         }
         // Ring protocol: the item lives in this (the scheduler's) CTA only; the leader's consumers fetch it with a
         // remote load after their own sched_full barrier fires.  All arrives use CTA-scope release (a cluster-scope
@@ -461,14 +406,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         ring[slot] = it;
         mbar_arrive(&sched_full[slot]);
         mbar_arrive_cluster(lead_sched_full + slot * 8);  // release at cluster scope: the slot is visible to the remote loads
-        const uint32_t used = slot, used_phase = sphase;
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
         if ((it.x & 0xff) == IT_END) break;
-        // a gather item keeps the pair's epilogue warps busy without any loads: wait until everybody has picked it up
-        // before popping another ticket, so that an idle scheduler cannot hoard gather items
-        if ((it.x & 0xff) == IT_GATHER) mbar_wait(&sched_empty[used], used_phase);
       }
-      if (tr) tr[11] = w_dep;
     }
     __syncwarp();
   } else if (warp == 0) {
@@ -487,7 +427,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         long long* ti = (tr && n_items < kTraceItems) ? tr + 16 + 4 * n_items : nullptr;
         if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; ti[1] = 0; }
         ++n_items;
-        if (kind == IT_GATHER) continue;
         const int n_blk = (it.x >> 8) & 0xff;
         const int rb = static_cast<int>(it.y);
         const P2Layer& ly = p.layer[kind];
@@ -495,11 +434,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const uint32_t bytes_pair = 2u * (L::kA + static_cast<uint32_t>(w_rows) * kBlockK * 2);
         const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
         const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
-        int kb0 = 0;
-        if (it.x & kItemPoll) {
-          // static item: its W tiles do not depend on anything -- put the first ring's worth in flight, then wait
-          // for the A operand's row block, then issue the matching A loads
-          const int npre = min(ly.num_kb, kP2Stages);
+        // the item's W tiles do not depend on anything: put the first ring's worth in flight, then wait for the A
+        // operand's row block, then issue the matching A loads
+        const int npre = min(ly.num_kb, kP2Stages);
+        {
           uint32_t st2 = stage, ph2 = phase;
           for (int kb = 0; kb < npre; ++kb) {
             if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[st2], ph2 ^ 1); w_empty += clock64() - t; }
@@ -508,20 +446,16 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             tma_load_2d_pair(smem + st2 * L::kStage + L::kA, &p.tm_w[kind], lead_full + st2 * 8, kb * kBlockK, w_row);
             if (++st2 == kP2Stages) { st2 = 0; ph2 ^= 1; }
           }
-          { const long long t = tr ? clock64() : 0;
-            p2_poll_dep(p, ly.dep_kind, rb);
-            if (tr) { w_dep += clock64() - t; if (ti) ti[1] = clock64(); } }
-          for (int kb = 0; kb < npre; ++kb) {
-            if (tr) t_issue[stage] = clock64();
-            tma_load_2d_pair(smem + stage * L::kStage, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
-            if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
-          }
-          kb0 = npre;
-        } else {
-          // pushed item: its inputs were complete before it was pushed; they are read by TMA only (async proxy)
-          fence_proxy_async_all();
         }
-        for (int kb = kb0; kb < ly.num_kb; ++kb) {
+        { const long long t = tr ? clock64() : 0;
+          p2_poll_dep(p, ly.dep_kind, rb);
+          if (tr) { w_dep += clock64() - t; if (ti) ti[1] = clock64(); } }
+        for (int kb = 0; kb < npre; ++kb) {
+          if (tr) t_issue[stage] = clock64();
+          tma_load_2d_pair(smem + stage * L::kStage, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
+          if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
+        }
+        for (int kb = npre; kb < ly.num_kb; ++kb) {
           if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStage;
@@ -548,7 +482,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
         const int kind = it.x & 0xff;
         if (kind == IT_END) break;
-        if (kind == IT_GATHER) continue;
         const P2Layer& ly = p.layer[kind];
         const uint32_t idesc = make_idesc_bf16(kP2Rows, static_cast<uint32_t>(ly.block_n));
         if (tr) { const long long t = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
@@ -586,64 +519,32 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
-    int pend_kind = -1, pend_rb = 0;   // previous tile's block: announced once its bulk stores have completed
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
-    // Deferred arrival: a tile's activation stores are announced (bulk-store completion wait + release increment of
-    // the block's counter) where this warp would otherwise idle -- while its next TMEM load is in flight, or before
-    // it blocks on the ring / an accumulator that is not ready yet.  It is never postponed past a point where the
-    // warp can block indefinitely: the item it would wait for may depend on exactly this arrival.
-    bool bias_ok = false;
-    long long pf_delay = 0, pf_wait = 0, pf_total = 0, pf_n = 0, t_pend = 0;
-    auto flush_pend = [&]() {
-      if (pend_kind >= 0) {
-        const long long t0 = (tr && threadIdx.x == 64) ? clock64() : 0;
-        p2_arrive(p, pend_kind, pend_rb, lane, true, (tr && threadIdx.x == 64) ? &pf_wait : nullptr);
-        pend_kind = -1;
-        if (tr && threadIdx.x == 64) { pf_delay += t0 - t_pend; pf_total += clock64() - t0; pf_n += 1; }
-      }
-    };
-    // phase 0: before it looks at the ring, this warp gathers its share of the first row blocks, one 4-row group per
-    // round (static assignment over all epilogue warps of the grid: no claim atomics)
-    int p0g = static_cast<int>(blockIdx.x) * kEpiWarps + wep;
-    const int p0step = static_cast<int>(gridDim.x) * kEpiWarps;
-    for (;;) {
-      long long group = -1;   // >= 0: a gather group to do in this iteration (phase 0 or a gather item)
-      int g_rb = 0;
-      uint2 it = make_uint2(IT_GATHER, 0u);
-      int kind = IT_GATHER;
-      if (p0g < p.phase0_groups) {
-        group = p0g; g_rb = p0g / kP2GroupsPerBlock; p0g += p0step;
-        if (tr && threadIdx.x == 64) tr[249] = clock64();
+    // phase 0: before it looks at the ring, this warp gathers its share of the rows, one 4-row group per round
+    // (static assignment over all epilogue warps of the grid: no claim atomics)
+    for (int g = static_cast<int>(blockIdx.x) * kEpiWarps + wep; g < p.phase0_groups; g += static_cast<int>(gridDim.x) * kEpiWarps) {
+      if (tr && threadIdx.x == 64) tr[249] = clock64();
+      if (FASTG) {
+        p2_gather_group_bulk(p.gather, g, lane, st);   // returns with the rows in global memory
+        if (tr && threadIdx.x == 64) tr[250] = clock64();
+        p2_arrive_done(p, DEP_X, g / kP2GroupsPerBlock, lane);
       } else {
-        if (tr && threadIdx.x == 64 && tr[5] == 0) tr[5] = clock64();
-        if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) flush_pend();
-        mbar_wait(&sched_full[slot], sphase);
-        it = ld_cluster_u32x2(ring_addr + slot * 8);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
-        if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
-        kind = it.x & 0xff;
-        if (kind == IT_END) { flush_pend(); break; }
-        if (kind == IT_GATHER) {
-          ++item_no;  // the producer numbers gather items too
-          g_rb = static_cast<int>(it.y);
-          group = static_cast<long long>(g_rb) * kP2GroupsPerBlock + ((it.x >> 8) & 0xff) * kP2WarpsPerPair + rank * kEpiWarps + wep;
-        }
+        pass_gather_group<2>(p.gather, g, lane);
+        if (tr && threadIdx.x == 64) tr[250] = clock64();
+        p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
       }
-      if (group >= 0) {
-        flush_pend();
-        if (FASTG) {
-          p2_gather_group_bulk(p.gather, group, lane, st);   // returns with the rows in global memory
-          if (tr && threadIdx.x == 64) tr[250] = clock64();
-          p2_arrive_done(p, DEP_X, g_rb, lane);
-        } else {
-          pass_gather_group<2>(p.gather, group, lane);
-          if (tr && threadIdx.x == 64) tr[250] = clock64();
-          p2_arrive(p, DEP_X, g_rb, lane, false);
-        }
-        continue;
-      }
-      if (!bias_ok) { mbar_wait(bias_bar, 0); bias_ok = true; }  // the bulk copies issued in the prologue have landed
+    }
+    if (tr && threadIdx.x == 64) tr[5] = clock64();
+    mbar_wait(bias_bar, 0);  // the bias bulk copies issued in the prologue have landed
+    long long pf_wait = 0, pf_total = 0, pf_n = 0;
+    for (;;) {
+      mbar_wait(&sched_full[slot], sphase);
+      const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
+      if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
+      const int kind = it.x & 0xff;
+      if (kind == IT_END) break;
       const int n_blk = (it.x >> 8) & 0xff;
       const int rb = static_cast<int>(it.y);
       long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
@@ -661,7 +562,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       unsigned long long trow_bits = 0ull;
       float4 tv2[8];
       if (want_cos) {
-        flush_pend();  // the staging tile may still be the source of an activation store of an earlier tile
         const float* trow = nullptr;
         if (row_ok) {
           long long tid = p.tail_idx[grow * p.tail_stride];
@@ -678,12 +578,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       }
       {
         const long long t = (tr && lane == 0) ? clock64() : 0;
-        if (pend_kind >= 0 && !__all_sync(0xffffffffu, mbar_test_wait(&tmem_full[acc], acc_phase))) flush_pend();
         mbar_wait(&tmem_full[acc], acc_phase);
         if (tr && lane == 0) { w_acc += clock64() - t; }
         if (ti) ti[2] = clock64();
       }
-      flush_pend();  // (no-op if done above) the previous tile's stores have had a whole accumulator wait to complete
       const long long t_busy0 = (tr && lane == 0) ? clock64() : 0;
       tc_fence_after();
 
@@ -761,9 +659,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
-        pend_kind = ly.out_kind; pend_rb = rb;
-        if (tr && threadIdx.x == 64) t_pend = clock64();
-        if (!pushing) flush_pend();  // small batch: the hand-off latency is on the critical path, do not defer it
+        // publish the tile: its bulk stores must have completed (a few hundred clocks: the hand-off latency is on the
+        // critical path of a small batch, so this is not deferred)
+        {
+          const long long t0 = (tr && threadIdx.x == 64) ? clock64() : 0;
+          p2_arrive(p, ly.out_kind, rb, lane, true, (tr && threadIdx.x == 64) ? &pf_wait : nullptr);
+          if (tr && threadIdx.x == 64) { pf_total += clock64() - t0; pf_n += 1; }
+        }
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block
@@ -991,7 +893,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
       tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
       tr[251] = ph_m1; tr[252] = ph_w2;
-      tr[245] = pf_delay; tr[246] = pf_wait; tr[247] = pf_total; tr[248] = pf_n;
+      tr[245] = 0; tr[246] = pf_wait; tr[247] = pf_total; tr[248] = pf_n;
     }
   }
 
@@ -1014,7 +916,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.ready[k * p.rb_cap + i] = 0;
     for (int k = 0; k < FIN_KINDS; ++k)
       for (int i = threadIdx.x; i < p.nrb; i += blockDim.x) p.fin[k * p.rb_cap + i] = 0;
-    for (int i = threadIdx.x; i < p.n_total - p.n_static; i += blockDim.x) p.queue[i] = 0ull;
     if (threadIdx.x == 0) { p.sched->q_head = 0; p.sched->q_tail = 0; p.sched->p0_next = 0; p.sched->init = 0; p.sched->done = 0; }
     if (tr && threadIdx.x == 0) { tr[13] = clock64(); tr[253] = static_cast<long long>(globaltimer_ns()); }
   }

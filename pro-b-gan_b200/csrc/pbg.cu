@@ -538,17 +538,12 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
   // phase 0: the first row blocks are gathered by the epilogue warps of all CTAs before the roles start (one 4-row
   // group per warp); the rest of the batch goes through gather items (64 rows each)
-  // Batches up to PBG_STATIC_MAX_RB row blocks run entirely from the static ticket list (phase 0 gathers every row,
-  // in as many rounds per warp as it takes); larger ones gather one round in phase 0 and push the rest.
-  static const int static_max_rb = [] { const char* e = getenv("PBG_STATIC_MAX_RB"); return e ? atoi(e) : 256; }();
-  p.p0_blocks = nrb <= static_max_rb ? nrb : std::min(nrb, std::max(1, grid * kEpiWarps / kP2GroupsPerBlock));
-  p.phase0_groups = p.p0_blocks * kP2GroupsPerBlock;
-  if (nrb <= p.p0_blocks) {
-    // small batch: every item is a static ticket, layer by layer (a topological order); the producers poll the
-    // dependency counters and nothing is pushed
-    // Waves: the row blocks are cut into `waves` groups and the layer phases of the groups are interleaved
-    // (L0 of every wave, then L1 of every wave, then L2), so that a pair waiting for one wave's hand-off has another
-    // wave's tiles next in its ticket sequence.
+  // phase 0 gathers every row (4-row groups, statically spread over the epilogue warps of the grid); every tile is
+  // a static ticket, layer by layer (a topological order): the producers poll the dependency counters.
+  p.phase0_groups = nrb * kP2GroupsPerBlock;
+  {
+    // Waves: the row blocks can be cut into `waves` groups whose layer phases are interleaved (L0 of every wave,
+    // then L1 of every wave, then L2).  One wave measured best at every size (PBG_WAVES to experiment).
     static const int waves_env = [] { const char* e = getenv("PBG_WAVES"); return e ? atoi(e) : 1; }();
     const int waves = std::max(1, std::min(waves_env, std::min(nrb, 3)));
     static const int phase_kinds[3][2] = {{IT_G_L0, IT_D_L0}, {IT_G_L1, IT_D_L1}, {IT_G_L2, -1}};
@@ -565,20 +560,14 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
         }
       }
     }
-    p.n_static = start;
     if (start != total) return fail(c, PBG_ERR_INVALID, "internal: static item list does not cover the pass");
-  } else {
-    total += static_cast<long long>(nrb - p.p0_blocks) * kP2GatherPerBlock;
+    p.n_total = start;
   }
-  p.n_total = static_cast<int>(total);
-  if (total - p.n_static > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
   p.gather = gp;
   static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
   p.poll_ns = poll_env;
-  static const int ahead_env = [] { const char* e = getenv("PBG_GATHER_AHEAD"); return e ? atoi(e) : 32; }();
-  p.gather_ahead = ahead_env;
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
-  p.queue = w.queue; p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
+  p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
   if (scores) {
     p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
