@@ -158,7 +158,8 @@ enum {
   PBG_K_D_L1 = 5,   /* discriminator Linear 1 (H -> H/2) + LeakyReLU + final dot + sigmoid */
   PBG_K_OTHER = 6,  /* fp32-mode row-dot / cosine, weight packing         */
   PBG_K_PASS = 7,   /* bf16 mode: the whole G + D pass as one persistent kernel (gather + 5 Linear layers) */
-  PBG_NUM_KERNEL_KINDS = 8
+  PBG_K_TOPK = 8,   /* entity scoring + top-k: the tensor-core filter kernel                               */
+  PBG_NUM_KERNEL_KINDS = 9
 };
 int pbg_profile_enable(pbg_ctx* ctx, int enable);
 int pbg_profile_read(pbg_ctx* ctx, double* ms, int64_t* count);
@@ -187,6 +188,19 @@ int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
  * Passes that cannot honour mirrors (fp32 mode, models too wide for the pair kernel) fail with PBG_ERR_UNSUPPORTED. */
 int pbg_set_result_mirrors(pbg_ctx* ctx, int n, void* const* gen_out, float* const* gen_scores,
                            float* const* logits, float* const* probs);
+
+/* Entity scoring + top-k: the tail of ProtBGANInference.predict_tails (pro_b_gan_infer.py:146-151) and all of
+ * find_similar_entities (:231-236):
+ *     similarities = F.normalize(queries, dim=-1) @ F.normalize(table, dim=-1).T      [B, N], never materialised
+ *     top_scores, top_indices = similarities.topk(k, dim=1)                           (largest first)
+ * pbg_topk_prepare reads the fp32 table [N, E] once (row norms + a normalised bf16 copy; the reference re-normalises
+ * all N rows on every call) -- call it again whenever the table changes.  pbg_topk scores fp32 queries [B, E] against
+ * the prepared table: bf16 tensor-core scores pick 32 candidates per (row, table slice), every candidate is re-scored
+ * exactly in fp32 and a row whose k-th exact score does not provably beat everything that was filtered out is redone
+ * by an exact scan, so indices / scores are those of an fp32 evaluation (ties between equal scores: lower index
+ * first).  out_idx int64 [B, k], out_scores fp32 [B, k]; 1 <= k <= 64 and k <= N.  Stream-ordered. */
+int pbg_topk_prepare(pbg_ctx* ctx, const float* table, int64_t N, void* stream);
+int pbg_topk(pbg_ctx* ctx, const float* queries, int64_t B, int k, int64_t* out_idx, float* out_scores, void* stream);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);

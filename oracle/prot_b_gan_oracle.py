@@ -114,3 +114,14 @@ class ModularDiscriminator(nn.Module):
 # runs (pro_b_gan_infer.py:93-94); see oracle/run_reference.py for the injection.
 Generator = ModularGenerator
 Discriminator = ModularDiscriminator
+
+
+def cosine_topk(queries: torch.Tensor, table: torch.Tensor, k: int):
+    """The entity-scoring tail of predict_tails / find_similar_entities, verbatim torch ops
+    (pro_b_gan_infer.py:146-151, :231-236): normalise both sides, full similarity matrix, topk.
+    Unlike the G / D graph above this part IS pinned by the reference: these are its own lines."""
+    import torch.nn.functional as F
+    q_norm = F.normalize(queries, dim=-1)
+    t_norm = F.normalize(table, dim=-1)
+    similarities = torch.matmul(q_norm, t_norm.T)
+    return similarities.topk(k, dim=1)

@@ -28,6 +28,7 @@
 #include "gemm_tc.cuh"
 #include "pass_kernel.cuh"
 #include "pass2_kernel.cuh"
+#include "topk_kernel.cuh"
 
 using namespace pbg;
 
@@ -74,6 +75,14 @@ struct ItemList {
   int phase0_groups = 0, p0_blocks = 0;
 };
 
+// entity scoring + top-k (pbg_topk_prepare / pbg_topk)
+struct TopkState {
+  const float* table = nullptr; long long N = 0, n_pad = 0;
+  __nv_bfloat16* tn = nullptr; float* inv_t = nullptr; CUtensorMap tm_t;
+  long long q_cap = 0; __nv_bfloat16* qn = nullptr; float* inv_q = nullptr; CUtensorMap tm_q;
+  size_t cand_cap = 0; float* cand_score = nullptr; int* cand_idx = nullptr; float* cand_tau = nullptr; int* flag = nullptr;
+};
+
 thread_local std::string g_create_error;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -100,6 +109,7 @@ struct pbg_ctx {
   long long* st_trip = nullptr;
   float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
   EncodeTiledFn encode = nullptr;
+  TopkState tk;
   std::map<std::tuple<long long, int, int>, ItemList> item_cache;  // (rows, run_g, run_d) -> work-item order
   long long launches = 0;
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
@@ -637,6 +647,117 @@ const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int pbg_topk_prepare(pbg_ctx* c, const float* table, int64_t N, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (!table || N <= 0) return fail(c, PBG_ERR_INVALID, "topk: null or empty table");
+  const int E = c->dims.embed_dim;
+  if (E % 4) return fail(c, PBG_ERR_UNSUPPORTED, "topk: embed_dim must be a multiple of 4");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  TopkState& t = c->tk;
+  const long long n_pad = (N + 255) / 256 * 256;
+  if (n_pad != t.n_pad) {
+    PBG_CUDA(c, cudaDeviceSynchronize());
+    cudaFree(t.tn); cudaFree(t.inv_t); t.tn = nullptr; t.inv_t = nullptr; t.n_pad = 0;
+    PBG_CUDA(c, cudaMalloc(&t.tn, sizeof(__nv_bfloat16) * n_pad * E));
+    PBG_CUDA(c, cudaMalloc(&t.inv_t, sizeof(float) * n_pad));
+    t.n_pad = n_pad;
+    if (E == 128) PBG_TRY(make_tmap(c, &t.tm_t, t.tn, n_pad, E, 128));
+  }
+  t.table = table; t.N = N;
+  { LaunchScope ls(c, PBG_K_OTHER, s);
+    topk_prepare_kernel<<<c->num_sms * 8, 256, 0, s>>>(table, N, n_pad, E, t.tn, t.inv_t); }
+  PBG_CUDA(c, cudaGetLastError());
+  return PBG_OK;
+}
+
+int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_idx, float* out_scores, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  TopkState& t = c->tk;
+  if (B < 0) return fail(c, PBG_ERR_INVALID, "negative batch");
+  if (B == 0) return PBG_OK;
+  if (!t.table) return fail(c, PBG_ERR_NOT_LOADED, "topk: no table prepared (pbg_topk_prepare)");
+  if (!queries || !out_idx || !out_scores) return fail(c, PBG_ERR_INVALID, "null tensor");
+  if (k < 1 || k > 64) return fail(c, PBG_ERR_UNSUPPORTED, "topk: k must be in [1, 64]");
+  if (k > t.N) return fail(c, PBG_ERR_INVALID, "topk: k = %d exceeds the %lld rows of the table", k, t.N);  // torch raises too
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int E = c->dims.embed_dim;
+  const long long kChunk = 16384;
+  const bool filter = E == 128 && k <= kTkMaxK && t.N >= 16 * 256;   // small tables: the exact scan is cheap
+  for (long long off = 0; off < B; off += kChunk) {
+    const long long rows = std::min(kChunk, B - off);
+    const long long rows_pad = (rows + 255) / 256 * 256;
+    const float* q = queries + off * E;
+    if (t.q_cap < rows_pad) {
+      PBG_CUDA(c, cudaDeviceSynchronize());
+      cudaFree(t.qn); cudaFree(t.inv_q); cudaFree(t.flag); t.qn = nullptr; t.inv_q = nullptr; t.flag = nullptr; t.q_cap = 0;
+      PBG_CUDA(c, cudaMalloc(&t.qn, sizeof(__nv_bfloat16) * rows_pad * E));
+      PBG_CUDA(c, cudaMalloc(&t.inv_q, sizeof(float) * rows_pad));
+      PBG_CUDA(c, cudaMalloc(&t.flag, sizeof(int) * rows_pad));
+      t.q_cap = rows_pad;
+      if (E == 128) PBG_TRY(make_tmap(c, &t.tm_q, t.qn, rows_pad, E, 128));
+    }
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_prepare_kernel<<<std::min<long long>(c->num_sms * 8, (rows_pad + 7) / 8), 256, 0, s>>>(q, rows, rows_pad, E, t.qn, t.inv_q); }
+    PBG_CUDA(c, cudaGetLastError());
+    long long* oi = reinterpret_cast<long long*>(out_idx) + off * k;
+    float* os = out_scores + off * k;
+    if (filter) {
+      const int grid = pass_grid(c) & ~1;
+      const int npairs = grid / 2;
+      TopkParams p;
+      memset(&p, 0, sizeof p);
+      p.tm_q = t.tm_q; p.tm_t = t.tm_t;
+      p.n_rb = static_cast<int>(rows_pad / 256);
+      p.n_tiles = static_cast<int>(t.n_pad / 256);
+      p.n_ranges = std::max(1, std::min({kTkMaxRanges, npairs / p.n_rb, p.n_tiles / kTkSample}));   // items <= pairs: one round
+      p.tiles_per_range = (p.n_tiles + p.n_ranges - 1) / p.n_ranges;
+      p.n_ranges = (p.n_tiles + p.tiles_per_range - 1) / p.tiles_per_range;   // no empty range
+      p.n_items = p.n_rb * p.n_ranges;
+      p.N = t.N;
+      const int n_lists = p.n_ranges * 2;
+      const size_t need = static_cast<size_t>(rows_pad) * n_lists * kTkCand;
+      if (t.cand_cap < need) {
+        PBG_CUDA(c, cudaDeviceSynchronize());
+        cudaFree(t.cand_score); cudaFree(t.cand_idx); cudaFree(t.cand_tau);
+        t.cand_score = nullptr; t.cand_idx = nullptr; t.cand_tau = nullptr; t.cand_cap = 0;
+        PBG_CUDA(c, cudaMalloc(&t.cand_score, sizeof(float) * need));
+        PBG_CUDA(c, cudaMalloc(&t.cand_idx, sizeof(int) * need));
+        PBG_CUDA(c, cudaMalloc(&t.cand_tau, sizeof(float) * need / kTkCand));
+        t.cand_cap = need;
+      }
+      p.cand_score = t.cand_score; p.cand_idx = t.cand_idx; p.cand_tau = t.cand_tau;
+      static int attr_dev = -1;
+      if (attr_dev != c->dims.device) {
+        PBG_CUDA(c, cudaFuncSetAttribute(pbg_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TkSmem::kTotal));
+        PBG_CUDA(c, cudaFuncSetAttribute(topk_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 4 + 8 * 2 * kTkMaxRanges * kTkCand * 8));
+        attr_dev = c->dims.device;
+      }
+      { LaunchScope ls(c, PBG_K_TOPK, s);
+        pbg_topk_filter_kernel<<<std::min(grid, 2 * p.n_items), kPassThreads, TkSmem::kTotal, s>>>(p); }
+      PBG_CUDA(c, cudaGetLastError());
+      { LaunchScope ls(c, PBG_K_OTHER, s);
+        topk_rescore_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 8 * 128 * 4 + 8 * n_lists * kTkCand * 8, s>>>(
+            q, t.inv_q, t.table, t.inv_t, t.cand_score, t.cand_idx, t.cand_tau, n_lists, rows, k, oi, os, t.flag); }
+      PBG_CUDA(c, cudaGetLastError());
+    }
+    {
+      static int attr_dev2 = -1;
+      if (attr_dev2 != c->dims.device) {
+        PBG_CUDA(c, cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 4 + 256 * 64 * 8));
+        attr_dev2 = c->dims.device;
+      }
+      // rows the filter could not prove (or every row when the filter does not apply): exact scan, one CTA per row
+      LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_exact_kernel<<<static_cast<unsigned>(rows), 256, E * 4 + 256 * k * 8, s>>>(q, t.inv_q, t.table, t.inv_t, t.N, E, k, t.flag,
+                                                                                     filter ? 0 : 1, oi, os);
+    }
+    PBG_CUDA(c, cudaGetLastError());
+  }
+  return PBG_OK;
+}
+
 int pbg_set_result_mirrors(pbg_ctx* c, int n, void* const* gen_out, float* const* gen_scores, float* const* logits,
                            float* const* probs) {
   if (!c) return PBG_ERR_INVALID;
@@ -720,6 +841,8 @@ void pbg_destroy(pbg_ctx* c) {
   cudaFree(c->d_w3); cudaFree(c->d_w3_pad);
   free_ws(c->ws_bf16); free_ws(c->ws_f32);
   cudaFree(c->err_flag); cudaFree(c->trace);
+  cudaFree(c->tk.tn); cudaFree(c->tk.inv_t); cudaFree(c->tk.qn); cudaFree(c->tk.inv_q);
+  cudaFree(c->tk.cand_score); cudaFree(c->tk.cand_idx); cudaFree(c->tk.cand_tau); cudaFree(c->tk.flag);
 
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
   cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);

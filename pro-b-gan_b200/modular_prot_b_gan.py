@@ -151,6 +151,28 @@ def make_fused_engine(generator: ModularGenerator, discriminator: ModularDiscrim
     return eng
 
 
+_TOPK_ENGINES: dict = {}
+
+
+def cosine_topk(queries: torch.Tensor, table: torch.Tensor, k: int):
+    """Drop-in for the entity-scoring lines of the reference script (pro_b_gan_infer.py:146-151 and :231-236):
+
+        pred_norm = F.normalize(pred_emb, dim=-1); entity_norm = F.normalize(self.node_emb, dim=-1)
+        similarities = torch.matmul(pred_norm, entity_norm.T); top_scores, top_indices = similarities.topk(top_k, dim=1)
+    becomes
+        top_scores, top_indices = modular_prot_b_gan.cosine_topk(pred_emb, self.node_emb, top_k)
+
+    CUDA tensors only (no CPU fallback).  One scoring ctx per (device, embedding width) is kept alive."""
+    if queries.device.type != "cuda" or table.device != queries.device:
+        raise RuntimeError("cosine_topk runs only on CUDA tensors on one device; there is no CPU fallback")
+    E = int(table.shape[1])
+    key = (queries.device.index, E)
+    eng = _TOPK_ENGINES.get(key)
+    if eng is None:
+        eng = _TOPK_ENGINES[key] = Engine(E, 8, 8, 16, queries.device, LEAKY_SLOPE)   # model dims unused by the scorer
+    return eng.cosine_topk(queries.detach(), table.detach(), k)
+
+
 # names the reference script instantiates (pro_b_gan_infer.py:93-94)
 Generator = ModularGenerator
 Discriminator = ModularDiscriminator

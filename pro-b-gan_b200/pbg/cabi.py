@@ -14,7 +14,7 @@ from . import build as _build
 PBG_OK, PBG_ERR_INVALID, PBG_ERR_CUDA, PBG_ERR_NOT_LOADED, PBG_ERR_INDEX, PBG_ERR_UNSUPPORTED, PBG_ERR_NOMEM = range(7)
 PREC_F32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-KERNEL_KINDS = ("gather", "g_l0", "g_l1", "g_l2", "d_l0", "d_l1", "other", "pass")
+KERNEL_KINDS = ("gather", "g_l0", "g_l1", "g_l2", "d_l0", "d_l1", "other", "pass", "topk")
 
 # every symbol include/pbg.h declares (tests check the .so exports exactly these)
 SYMBOLS = (
@@ -22,7 +22,7 @@ SYMBOLS = (
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
-    "pbg_set_launch_width", "pbg_set_result_mirrors",
+    "pbg_set_launch_width", "pbg_set_result_mirrors", "pbg_topk_prepare", "pbg_topk",
 )
 
 
@@ -73,6 +73,8 @@ def load() -> C.CDLL:
         "pbg_launch_count": (i64, [vp]),
         "pbg_set_launch_width": (C.c_int, [vp, i32]),
         "pbg_set_result_mirrors": (C.c_int, [vp, i32, vp, vp, vp, vp]),
+        "pbg_topk_prepare": (C.c_int, [vp, vp, i64, vp]),
+        "pbg_topk": (C.c_int, [vp, vp, i64, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

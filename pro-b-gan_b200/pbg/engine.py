@@ -75,6 +75,25 @@ class Engine:
         """CTAs (SMs) one fused pass occupies; 0 = the whole device.  See include/pbg.h."""
         cabi.check(self._lib.pbg_set_launch_width(self._h, int(ctas)), self._h)
 
+    def cosine_topk(self, queries: torch.Tensor, table: torch.Tensor, k: int):
+        """``F.normalize(queries) @ F.normalize(table).T`` followed by ``.topk(k, dim=1)`` without the [B, N] matrix
+        (pro_b_gan_infer.py:146-151, :231-236).  Returns (scores fp32 [B, k], indices int64 [B, k]) like torch.topk.
+        The prepared (normalised) table is cached until the tensor is modified or another table is passed."""
+        table = self._f32(table, self.E, "table")
+        queries = self._f32(queries, self.E, "queries")
+        if k > table.shape[0]:
+            raise RuntimeError(f"selected index k out of range: k = {k} > {table.shape[0]} rows")  # what torch.topk raises
+        key = (table.data_ptr(), tuple(table.shape), table._version)
+        with torch.cuda.device(self.device):
+            if getattr(self, "_topk_key", None) != key:
+                cabi.check(self._lib.pbg_topk_prepare(self._h, _ptr(table), table.shape[0], self._stream()), self._h)
+                self._topk_key, self._topk_table = key, table   # keep the tensor alive while the ctx refers to it
+            B = queries.shape[0]
+            scores = torch.empty(B, k, dtype=torch.float32, device=self.device)
+            idx = torch.empty(B, k, dtype=torch.int64, device=self.device)
+            cabi.check(self._lib.pbg_topk(self._h, _ptr(queries), B, int(k), _ptr(idx), _ptr(scores), self._stream()), self._h)
+        return scores, idx
+
     def set_result_mirrors(self, gen_out=(), gen_scores=(), logits=(), probs=()) -> None:
         """Device addresses (ints) of up to 7 mirror buffers per result, e.g. peer GPUs' windows: every bf16-mode
         pass also writes its rows there (include/pbg.h: pbg_set_result_mirrors).  Empty lists clear."""

@@ -145,3 +145,14 @@ def test_reference_script_as_shipped_needs_the_seam(synthetic_ckpt, oracle):
             ref.ProtBGANInference(synthetic_ckpt, "cpu")
     finally:
         sys.modules.pop("modular_prot_b_gan", None)
+
+
+def test_oracle_cosine_topk_reproduces_the_reference_scripts_predict_tails(gold, tables):
+    """oracle.cosine_topk restates pro_b_gan_infer.py:146-151; fed the fixture's generator outputs it must give the
+    indices / scores the UNMODIFIED reference script printed for --task predict_tails (config1_predict_tails.json)."""
+    from oracle import prot_b_gan_oracle as oracle
+    want = json.loads((GOLDEN / "config1_predict_tails.json").read_text())
+    node_emb, _ = tables
+    scores, idx = oracle.cosine_topk(gold["gen_out"], node_emb, want["metadata"]["top_k"])
+    assert idx.tolist() == want["predictions"]
+    assert (scores - torch.tensor(want["scores"])).abs().max().item() <= ATOL

@@ -1,0 +1,44 @@
+"""Entity scoring + top-k (predict_tails tail, pro_b_gan_infer.py:146-151): this repo's fused path against the
+reference's own torch lines on the same GPU (cuBLAS fp32 matmul + torch.topk) and on the host CPU."""
+import sys, time
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT / "pro-b-gan_b200"), str(ROOT)]
+import torch
+import torch.nn.functional as F
+import modular_prot_b_gan as m
+
+dev = torch.device("cuda:0")
+k = 10
+for B, N in ((4096, 65536), (256, 65536), (16, 65536), (16384, 65536)):
+    g = torch.Generator().manual_seed(B + N)
+    q, t = torch.randn(B, 128, generator=g).to(dev), torch.randn(N, 128, generator=g).to(dev)
+
+    def ours():
+        return m.cosine_topk(q, t, k)
+
+    def torch_lines():
+        return torch.matmul(F.normalize(q, dim=-1), F.normalize(t, dim=-1).T).topk(k, dim=1)
+
+    res = {}
+    for name, fn in (("fused", ours), ("torch-on-gpu", torch_lines)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        e0.record()
+        for _ in range(n):
+            out = fn()
+        e1.record(); torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / n * 1e3
+    same = torch.equal(ours()[1], torch_lines()[1])
+    eng = m._TOPK_ENGINES[(0, 128)]
+    eng.profile_enable(True); eng.profile_read()
+    for _ in range(5):
+        ours()
+    prof = {k_: round(v[0] / max(v[1], 1) * 1e3, 1) for k_, v in eng.profile_read().items() if v[1]}
+    eng.profile_enable(False)
+    flop = 2.0 * B * N * 128
+    print(f"B={B:6d} N={N}: fused {res['fused']:9.1f} us ({flop / res['fused'] / 1e6:7.1f} TFLOP/s, {B / res['fused']:.2f} M queries/s)   "
+          f"torch lines on the same GPU {res['torch-on-gpu']:9.1f} us   x{res['torch-on-gpu'] / res['fused']:.1f}   indices identical: {same}   us per launch by kind {prof}", flush=True)
