@@ -520,9 +520,15 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
-    // phase 0: before it looks at the ring, this warp gathers its share of the rows, one 4-row group per round
-    // (static assignment over all epilogue warps of the grid: no claim atomics)
-    for (int g = static_cast<int>(blockIdx.x) * kEpiWarps + wep; g < p.phase0_groups; g += static_cast<int>(gridDim.x) * kEpiWarps) {
+    // phase 0: before it looks at the ring, this warp gathers rows, one 4-row group per round, claimed from a counter.
+    // (Claimed, not statically assigned: like the tickets, the gather must not depend on CTAs of this launch that are
+    // not resident yet -- several launches may share the device, and whatever subset of a launch's CTAs is running has
+    // to be able to finish the pass on its own.)
+    for (;;) {
+      int g = 0;
+      if (lane == 0) g = atomicAdd(&p.sched->p0_next, 1);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= p.phase0_groups) break;
       if (tr && threadIdx.x == 64) tr[249] = clock64();
       if (FASTG) {
         p2_gather_group_bulk(p.gather, g, lane, st);   // returns with the rows in global memory
@@ -888,7 +894,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (ti) ti[3] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    tma_store_wait<0>();  // nothing of this warp's staging (any lane's bulk stores) may be in flight when the CTA exits
+    // every lane: its bulk stores must have READ the staging tile before the CTA (and its shared memory) goes away; their
+    // global / peer writes complete with the grid -- waiting for them here would put an NVLink round trip on every CTA's exit
+    tma_store_wait_read<0>();
     if (tr && threadIdx.x == 64) {
       tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
       tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
