@@ -77,8 +77,7 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
         P(f"   TANH epilogue (warp 2, last tile): start -> tmem loaded {(tt[:, 233] - tt[:, 232]).mean():.0f}  tanh {(tt[:, 234] - tt[:, 233]).mean():.0f}"
           f"  cosine {(tt[:, 235] - tt[:, 234]).mean():.0f}  output {(tt[:, 236] - tt[:, 235]).mean():.0f}")
     pfn = ph[:, 8].clamp_min(1)
-    P(f"   deferred arrival (warp 2, clk per tile): epilogue end -> flush {(ph[:, 5] / pfn).mean():.0f}  bulk-store completion wait {(ph[:, 6] / pfn).mean():.0f}"
-      f"  whole flush {(ph[:, 7] / pfn).mean():.0f}")
+    P(f"   tile hand-off (warp 2, clk per tile): bulk-store completion wait {(ph[:, 6] / pfn).mean():.0f}  whole arrival {(ph[:, 7] / pfn).mean():.0f}")
     gsel = ph[:, 9] > 0
     if gsel.any():
         P(f"   phase-0 gather (warp 2): start@ {(ph[:, 9] - hdr[:, 0])[gsel].mean():.0f}  loads+stores issued@ {(ph[:, 10] - hdr[:, 0])[gsel].mean():.0f}"
