@@ -301,7 +301,9 @@ __device__ __forceinline__ uint32_t ring_dep(uint2 it) { return (it.x >> 24) << 
 
 // TR: the diagnostics instance (pbg_debug_trace); the production instance carries no trace code or registers.
 // FASTG: the gather only carries the E = 128, Z <= 128 register path (the host checks the dims).
-template <bool TR, bool FASTG>
+// BIASS: biases + final dot weights are copied to shared memory in the prologue (they fit for H <= 1024); without it
+//        (wide models: long main loops, the epilogue is off the critical path) they are read through the global path.
+template <bool TR, bool FASTG, bool BIASS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPassThreads, 1)
 pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   using L = P2Smem;
@@ -352,6 +354,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     }
     mbar_init(bias_bar, 1);
     fence_mbar_init();
+    if (BIASS) {
     // Biases (and the final dot weights) live in shared memory for the whole launch: with ~224 KB of the SM carved out
     // as shared memory a bias read through the global path is an L2 round trip.  One bulk copy per array, in flight
     // while the rest of the prologue and the gather run; the epilogue warps wait for them once.
@@ -365,6 +368,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         bulk_load_1d(sbias + p.layer[k].bias_off, p.layer[k].bias, static_cast<uint32_t>(p.layer[k].n_tiles * p.layer[k].block_n) * 4u, bias_bar);
     if (p.layer_mask & (1u << IT_D_L1))
       bulk_load_1d(sbias + p.w3_off, p.w3, static_cast<uint32_t>(p.layer[IT_D_L1].n_tiles * p.layer[IT_D_L1].block_n) * 4u, bias_bar);
+    }
   }
   if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
@@ -541,7 +545,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       }
     }
     if (tr && threadIdx.x == 64) tr[5] = clock64();
-    mbar_wait(bias_bar, 0);  // the bias bulk copies issued in the prologue have landed
+    if (BIASS) mbar_wait(bias_bar, 0);  // the bias bulk copies issued in the prologue have landed
     long long pf_wait = 0, pf_total = 0, pf_n = 0;
     for (;;) {
       mbar_wait(&sched_full[slot], sphase);
@@ -596,7 +600,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const bool tp = tr && threadIdx.x == 64;
         long long tq0 = 0, tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq5 = 0, tq6 = 0;
         const float slope = p.slope;
-        const float* const bias_tile = sbias + ly.bias_off + n0;  // shared memory (the host guarantees bias_off >= 0)
+        const float* const bias_tile = (BIASS ? sbias + ly.bias_off : ly.bias) + n0;
         const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
         // 32-column TMEM loads, software pipelined: the next load is in flight while the previous one is converted
         uint32_t va[32], vb[32];
@@ -681,8 +685,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
-          const float4* b4 = reinterpret_cast<const float4*>(sbias + ly.bias_off + n0 + c * 64);
-          const float4* w4 = reinterpret_cast<const float4*>(sbias + p.w3_off + n0 + c * 64);
+          const float4* b4 = reinterpret_cast<const float4*>((BIASS ? sbias + ly.bias_off : ly.bias) + n0 + c * 64);
+          const float4* w4 = reinterpret_cast<const float4*>((BIASS ? sbias + p.w3_off : p.w3) + n0 + c * 64);
           tmem_ld_wait();
           if (c + 2 >= n_chunks) {
             tc_fence_before();
@@ -753,7 +757,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           uint32_t v[64];
           tmem_ld_32x32_ptr(taddr + c * 64, v);
           tmem_ld_32x32_ptr(taddr + c * 64 + 32, v + 32);
-          const float4* b4 = reinterpret_cast<const float4*>(sbias + ly.bias_off + col0);
+          const float4* b4 = reinterpret_cast<const float4*>((BIASS ? sbias + ly.bias_off : ly.bias) + col0);
           tmem_ld_wait();
           if (c + 2 >= n_chunks) {
             tc_fence_before();

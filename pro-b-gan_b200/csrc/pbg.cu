@@ -393,12 +393,8 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
 
   if (bf) {
     static const bool force_v1 = [] { const char* e = getenv("PBG_PASS_V1"); return e && atoi(e) != 0; }();
-    // the pair kernel keeps every bias in shared memory; wider models take the single-CTA kernel
-    int bias_floats = 0;
-    if (a.run_g) bias_floats += c->g[0].np + c->g[1].np + c->g[2].np;
-    if (a.run_d) bias_floats += c->d[0].np + 2 * c->d[1].np;
-    const bool use_v1 = force_v1 || bias_floats > P2Smem::kBiasFloats;
-    if (use_v1 && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors need the pair kernel (model too wide)");
+    const bool use_v1 = force_v1;  // the r1b single-CTA kernel, kept for A/B runs
+    if (use_v1 && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors need the pair kernel");
     return use_v1 ? launch_pass(c, w, a, gp, off, rows, gen_out, scores)
                   : launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
   } else {
@@ -489,9 +485,9 @@ int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp,
   return PBG_OK;
 }
 
-template <bool TR, bool FASTG>
+template <bool TR, bool FASTG, bool BIASS>
 cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s, bool pdl) {
-  auto kern = pbg_pass2_kernel<TR, FASTG>;
+  auto kern = pbg_pass2_kernel<TR, FASTG, BIASS>;
   static int attr_dev = -1;  // per instantiation; ctxs on different devices share the function handle
   if (attr_dev != c->dims.device) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P2Smem::kTotal);
@@ -536,13 +532,14 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     p.layer_mask |= 1u << k;
     total += static_cast<long long>(nrb) * (l.np / bn);
   }
-  // biases + final dot weights are copied to shared memory at kernel start (pass2_fits checked that they fit)
+  // biases + final dot weights are copied to shared memory at kernel start when they fit (H <= 1024)
+  bool biass = false;
   {
     int off = 0;
     for (int k = 0; k < 5; ++k) if (on[k]) { p.layer[k].bias_off = off; off += lin[k]->np; }
     p.w3_off = off;
     if (on[IT_D_L1]) off += lin[IT_D_L1]->np;
-    if (off > P2Smem::kBiasFloats) return fail(c, PBG_ERR_INVALID, "internal: biases do not fit the pair kernel's shared memory");
+    biass = off <= P2Smem::kBiasFloats;
   }
   if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
@@ -606,12 +603,21 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
                      c->kg0p == c->kg0 && c->kd0p == c->kd0;  // the bulk-store gather writes unpadded rows
   cudaError_t le;
   { LaunchScope ls(c, PBG_K_PASS, a.stream);
-    if (p.trace) le = fastg ? launch_p2<true, true>(c, p, grid, a.stream, pdl) : launch_p2<true, false>(c, p, grid, a.stream, pdl);
-    else le = fastg ? launch_p2<false, true>(c, p, grid, a.stream, pdl) : launch_p2<false, false>(c, p, grid, a.stream, pdl); }
+    const int sel = (p.trace ? 4 : 0) | (fastg ? 2 : 0) | (biass ? 1 : 0);
+    switch (sel) {
+      case 0: le = launch_p2<false, false, false>(c, p, grid, a.stream, pdl); break;
+      case 1: le = launch_p2<false, false, true>(c, p, grid, a.stream, pdl); break;
+      case 2: le = launch_p2<false, true, false>(c, p, grid, a.stream, pdl); break;
+      case 3: le = launch_p2<false, true, true>(c, p, grid, a.stream, pdl); break;
+      case 4: le = launch_p2<true, false, false>(c, p, grid, a.stream, pdl); break;
+      case 5: le = launch_p2<true, false, true>(c, p, grid, a.stream, pdl); break;
+      case 6: le = launch_p2<true, true, false>(c, p, grid, a.stream, pdl); break;
+      default: le = launch_p2<true, true, true>(c, p, grid, a.stream, pdl); break;
+    } }
   if (le == cudaSuccess) le = cudaGetLastError();
   if (le != cudaSuccess) {
     cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false, true>);
+    cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false, true, true>);
     return fail(c, PBG_ERR_CUDA, "pass kernel launch failed: %s (grid %d x %d threads, %d regs/thread, %zu B static + %d B dynamic smem, "
                 "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kPassThreads, fa.numRegs,
                 fa.sharedSizeBytes, P2Smem::kTotal, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);

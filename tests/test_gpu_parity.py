@@ -373,3 +373,28 @@ def test_result_mirrors_receive_the_same_rows(cuda_models, dev_tables, synth, de
     eng.set_result_mirrors()
     res2 = _pass(eng, dev_tables, trip, z)
     assert torch.equal(res2["logits"], res["logits"])
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[4]: the width-scaled model
+def test_wide_model_config5_matches_oracle(synth, dev):
+    """E = 256, H = 4096 (SURVEY.md 8d's reading of "4x channels, 2x output resolution"), per-GPU batch 1024: the same
+    pair kernel (biases through the global path: they no longer fit shared memory) against the fp32 oracle."""
+    import modular_prot_b_gan as m
+    from oracle import prot_b_gan_oracle as oracle
+    E, Z, H, B, N = 256, 64, 4096, 1024, 8192
+    Go, Do = synth.make_models(oracle.ModularGenerator, oracle.ModularDiscriminator, E, Z, H, H)
+    G, D = synth.make_models(m.ModularGenerator, m.ModularDiscriminator, E, Z, H, H)
+    node_emb, rel_w = synth.make_tables(N, 64, E)
+    trip, z = synth.make_triplets(B, N, 64), synth.make_latents(B, Z)
+    with torch.no_grad():
+        h, r, t = node_emb[trip[:, 0]], rel_w[trip[:, 1]], node_emb[trip[:, 2]]
+        g, d = Go(h, r, z), Do(h, r, t)
+        cs = F.cosine_similarity(g, t, dim=1)
+    eng = m.make_fused_engine(G.to(dev), D.to(dev))
+    res = eng.score_triplets(node_emb.to(dev), rel_w.to(dev), trip.to(dev), z.to(dev), want_gen_out=True,
+                             want_gen_scores=True, want_disc=True, precision="bf16")
+    eng.check_indices()
+    assert rel_err(res["gen_out"].cpu(), g) <= BF16_REL
+    assert rel_err(res["logits"].cpu(), d) <= BF16_REL
+    assert (res["probs"].cpu() - torch.sigmoid(d)).abs().max().item() <= BF16_REL
+    assert (res["gen_scores"].cpu() - cs).abs().max().item() <= BF16_REL
