@@ -524,15 +524,17 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
-    // phase 0: before it looks at the ring, this warp gathers rows, one 4-row group per round, claimed from a counter.
-    // (Claimed, not statically assigned: like the tickets, the gather must not depend on CTAs of this launch that are
-    // not resident yet -- several launches may share the device, and whatever subset of a launch's CTAs is running has
-    // to be able to finish the pass on its own.)
-    for (;;) {
+    // The gather: 4-row groups claimed from a counter (claimed, not statically assigned: like the tickets, nothing may
+    // depend on CTAs of this launch that are not resident yet -- several launches may share the device, and whatever
+    // subset of a launch's CTAs is running has to be able to finish the pass on its own).  A warp gathers whenever it
+    // would otherwise wait -- for a ring item, for an accumulator -- so only the first groups sit in front of the
+    // first tiles; the counter hands the groups out in row order, which is the order the tiles need them in.
+    bool more_groups = true;
+    auto gather_one = [&]() {   // warp-uniform; false once every group has been claimed
       int g = 0;
       if (lane == 0) g = atomicAdd(&p.sched->p0_next, 1);
       g = __shfl_sync(0xffffffffu, g, 0);
-      if (g >= p.phase0_groups) break;
+      if (g >= p.phase0_groups) { more_groups = false; return; }
       if (tr && threadIdx.x == 64) tr[249] = clock64();
       if (FASTG) {
         p2_gather_group_bulk(p.gather, g, lane, st);   // returns with the rows in global memory
@@ -543,11 +545,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (tr && threadIdx.x == 64) tr[250] = clock64();
         p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
       }
-    }
-    if (tr && threadIdx.x == 64) tr[5] = clock64();
-    if (BIASS) mbar_wait(bias_bar, 0);  // the bias bulk copies issued in the prologue have landed
+    };
+    gather_one();   // everybody starts with one group: nothing else can be ready yet
+    bool bias_ok = !BIASS;
     long long pf_wait = 0, pf_total = 0, pf_n = 0;
     for (;;) {
+      while (more_groups && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) gather_one();
       mbar_wait(&sched_full[slot], sphase);
       const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
       __syncwarp();
@@ -555,6 +558,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
       const int kind = it.x & 0xff;
       if (kind == IT_END) break;
+      // idle until this item's accumulator is ready: gather (the staging tile is free between tiles)
+      while (more_groups && !__all_sync(0xffffffffu, mbar_test_wait(&tmem_full[acc], acc_phase))) gather_one();
+      if (tr && threadIdx.x == 64 && tr[5] == 0) tr[5] = clock64();
+      if (!bias_ok) { mbar_wait(bias_bar, 0); bias_ok = true; }  // the bias bulk copies issued in the prologue have landed
       const int n_blk = (it.x >> 8) & 0xff;
       const int rb = static_cast<int>(it.y);
       long long* ti = (tr && threadIdx.x == 64 && item_no < kTraceItems) ? tr + 16 + 4 * item_no : nullptr;
