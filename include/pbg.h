@@ -165,7 +165,7 @@ int pbg_profile_enable(pbg_ctx* ctx, int enable);
 int pbg_profile_read(pbg_ctx* ctx, double* ms, int64_t* count);
 
 /* Diagnostics: while enabled, the tensor-core kernels write clock64 slots per CTA (begin, producer / MMA /
- * epilogue wait sums, end stamps and a per-item timeline; layout in pass_kernel.cuh) into a device buffer of
+ * epilogue wait sums, end stamps and a per-item timeline; layout in pass2_kernel.cuh) into a device buffer of
  * 256 x num_SMs slots.
  * The call synchronises the device, copies the current slots to host_out (if non-NULL, up to n_slots),
  * then enables / disables tracing and zeroes the buffer. */

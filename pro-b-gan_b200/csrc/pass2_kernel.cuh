@@ -32,7 +32,7 @@
 #include "ptx.cuh"
 #include "gather.cuh"
 #include "gemm_tc.cuh"
-#include "pass_kernel.cuh"
+#include "pass_common.cuh"
 
 namespace pbg {
 

@@ -26,7 +26,7 @@
 #include "gather.cuh"
 #include "gemm_f32.cuh"
 #include "gemm_tc.cuh"
-#include "pass_kernel.cuh"
+#include "pass_common.cuh"
 #include "pass2_kernel.cuh"
 #include "topk_kernel.cuh"
 
@@ -65,14 +65,6 @@ struct Workspace {
   PassSched* sched = nullptr;
   float* part_g = nullptr;  // [mb_cap][4][3][128]
   float* part_d = nullptr;  // [mb_cap][2 * max n_tiles][128]
-  unsigned long long* queue = nullptr;  // ready queue, zero between launches
-  long long queue_cap = 0;
-};
-
-struct ItemList {
-  int n = 0;  // work items per launch
-  int block_n[5] = {128, 128, 128, 128, 128};
-  int phase0_groups = 0, p0_blocks = 0;
 };
 
 // entity scoring + top-k (pbg_topk_prepare / pbg_topk)
@@ -110,7 +102,6 @@ struct pbg_ctx {
   float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
   EncodeTiledFn encode = nullptr;
   TopkState tk;
-  std::map<std::tuple<long long, int, int>, ItemList> item_cache;  // (rows, run_g, run_d) -> work-item order
   long long launches = 0;
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
   int n_mirror = 0;     // pbg_set_result_mirrors
@@ -181,7 +172,7 @@ void free_linear(Linear& l) {
 
 void free_ws(Workspace& w) {
   cudaFree(w.xg0); cudaFree(w.xd0); cudaFree(w.bufA); cudaFree(w.bufB); cudaFree(w.bufD);
-  cudaFree(w.ready); cudaFree(w.fin); cudaFree(w.sched); cudaFree(w.part_g); cudaFree(w.part_d); cudaFree(w.queue);
+  cudaFree(w.ready); cudaFree(w.fin); cudaFree(w.sched); cudaFree(w.part_g); cudaFree(w.part_d);
   w = Workspace{};
 }
 
@@ -237,11 +228,6 @@ int ensure_ws(pbg_ctx* c, int prec, long long rows) {
     PBG_CUDA(c, cudaMemset(w.ready, 0, sizeof(int) * DEP_KINDS * w.mb_cap));
     PBG_CUDA(c, cudaMemset(w.fin, 0, sizeof(int) * FIN_KINDS * w.mb_cap));
     PBG_CUDA(c, cudaMemset(w.sched, 0, sizeof(PassSched)));
-    // every row block contributes at most: 128-wide tiles of all five layers + 4 gather items
-    w.queue_cap = static_cast<long long>(w.mb_cap) *
-                  (2 * (c->hgp / 128) + c->hdp / 128 + c->hd2p / 128 + c->ep / 128 + kGatherPerBlock) + 64;
-    PBG_CUDA(c, cudaMalloc(&w.queue, sizeof(unsigned long long) * w.queue_cap));
-    PBG_CUDA(c, cudaMemset(w.queue, 0, sizeof(unsigned long long) * w.queue_cap));
     PBG_TRY(make_tmap(c, &w.tm_xg0, w.xg0, cap, c->kg0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_xd0, w.xd0, cap, c->kd0p, kBlockM));
     PBG_TRY(make_tmap(c, &w.tm_bufA_g, w.bufA, cap, c->hgp, kBlockM));
@@ -298,11 +284,6 @@ int launch_f32(pbg_ctx* c, int kind, const Linear& l, const float* A, long long 
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Tiling plan of the fused pass kernel for one batch size: tile width per layer, how many row blocks phase 0
-// gathers, and the number of work items the launch will push through its ready queue.
-struct LayerPlan { int num_kb, bn, n_tiles; };
-
 // CTAs per launch of the pass kernel: one per SM unless PBG_GRID asks for fewer (several streams sharing the GPU)
 int pass_grid(const pbg_ctx* c) {
   static const int env = [] { const char* e = getenv("PBG_GRID"); return e ? atoi(e) : 0; }();
@@ -310,44 +291,7 @@ int pass_grid(const pbg_ctx* c) {
   return (want > 0 && want < c->num_sms) ? std::max(2, want) : c->num_sms;
 }
 
-int build_items(pbg_ctx* c, long long rows, bool run_g, bool run_d, ItemList** out) {
-  const auto key = std::make_tuple(rows, static_cast<int>(run_g), static_cast<int>(run_d));
-  auto hit = c->item_cache.find(key);
-  if (hit != c->item_cache.end()) { *out = &hit->second; return PBG_OK; }
-  if (c->item_cache.size() >= 256) c->item_cache.clear();
-  const int mb = static_cast<int>((rows + kBlockM - 1) / kBlockM);
-  const int P = pass_grid(c);
-  const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
-  const bool on[5] = {run_g, run_d, run_g, run_d, run_g};
-  ItemList il;
-  long long total = 0;
-  for (int k = 0; k < 5; ++k) {
-    if (!on[k]) continue;
-    int bn = lin[k]->block_n;
-    if (bn == 256 && static_cast<long long>(mb) * (lin[k]->np / 256) < P / 2) bn = 128;  // small batch: finer tiles
-    il.block_n[k] = bn;
-    if (lin[k]->np / bn > 255) return fail(c, PBG_ERR_UNSUPPORTED, "layer too wide for the tile index");
-    total += static_cast<long long>(mb) * (lin[k]->np / bn);
-  }
-  if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
-  if (on[IT_G_L2] && lin[IT_G_L2]->np / 32 > kPartSlotsG) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
-  // phase 0: the first row blocks are gathered by all warps before the roles start, one 4-row group per warp and
-  // round; the rest of the batch goes through gather items (32 rows each)
-  il.p0_blocks = std::min(mb, P * (kPassThreads / 32) / 32);
-  il.phase0_groups = il.p0_blocks * 32;
-  for (int m = il.p0_blocks; m < mb; ++m) {
-    const long long r = std::min<long long>(kBlockM, rows - static_cast<long long>(m) * kBlockM);
-    total += (r + kGatherRows - 1) / kGatherRows;
-  }
-  il.n = static_cast<int>(total);
-  auto ins = c->item_cache.emplace(key, il);
-  *out = &ins.first->second;
-  return PBG_OK;
-}
-
 struct Pass;
-int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                void* gen_out, float* scores);
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
                  void* gen_out, float* scores);
 
@@ -392,11 +336,7 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
 
   if (bf) {
-    static const bool force_v1 = [] { const char* e = getenv("PBG_PASS_V1"); return e && atoi(e) != 0; }();
-    const bool use_v1 = force_v1;  // the r1b single-CTA kernel, kept for A/B runs
-    if (use_v1 && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors need the pair kernel");
-    return use_v1 ? launch_pass(c, w, a, gp, off, rows, gen_out, scores)
-                  : launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
+    return launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
   } else {
     float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
     const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
@@ -426,64 +366,6 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   return PBG_OK;
 }
 
-
-int launch_pass(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                void* gen_out, float* scores) {
-  ItemList* il = nullptr;
-  PBG_TRY(build_items(c, rows, a.run_g, a.run_d, &il));
-  static bool attr_set = false;
-  static int attr_dev = -1;
-  if (!attr_set || attr_dev != c->dims.device) {
-    PBG_CUDA(c, cudaFuncSetAttribute(pbg_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PassSmem::kTotal));
-    attr_set = true; attr_dev = c->dims.device;
-  }
-  PassParams p;
-  memset(&p, 0, sizeof p);
-  const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
-  const CUtensorMap* amap[5] = {&w.tm_xg0, &w.tm_xd0, &w.tm_bufA_g, &w.tm_bufD_d, &w.tm_bufB_g};
-  const CUtensorMap* omap[5] = {&w.tmo_bufA, &w.tmo_bufD, &w.tmo_bufB, nullptr, nullptr};
-  const bool on[5] = {a.run_g, a.run_d, a.run_g, a.run_d, a.run_g};
-  static const int pred_of[5] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1};
-  static const int out_of[5] = {DEP_G0, DEP_D0, DEP_G1, -1, -1};
-  static const int epi_of[5] = {PEPI_STORE, PEPI_STORE, PEPI_STORE, PEPI_ROWDOT, PEPI_TANH};
-  __nv_bfloat16* outs[5] = {(__nv_bfloat16*)w.bufA, (__nv_bfloat16*)w.bufD, (__nv_bfloat16*)w.bufB, nullptr, nullptr};
-  const int ldos[5] = {c->hgp, c->hdp, c->hgp, 0, 0};
-  for (int k = 0; k < 5; ++k) {
-    if (!on[k]) continue;
-    const Linear& l = *lin[k];
-    const int bn = il->block_n[k];
-    p.tm_a[k] = *amap[k];
-    p.tm_w[k] = (bn == l.block_n) ? l.tmap_w : l.tmap_w128;
-    if (omap[k]) p.tm_o[k] = *omap[k];
-    p.layer[k] = PassLayer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], ldos[k], 0, l.b_pad, outs[k]};
-    p.layer_mask |= 1u << k;
-  }
-  p.gather = gp;
-  static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
-  p.poll_ns = poll_env;
-  p.phase0_groups = il->phase0_groups; p.p0_blocks = il->p0_blocks; p.gather_ahead = 32;
-  p.mb = static_cast<int>((rows + kBlockM - 1) / kBlockM);
-  p.queue = w.queue; p.n_total = il->n;
-  if (il->n > w.queue_cap) return fail(c, PBG_ERR_INVALID, "internal: ready queue too small");
-  p.M = static_cast<int>(rows); p.mb_cap = w.mb_cap; p.slope = c->dims.leaky_slope;
-  p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
-  p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
-  if (scores) {
-    p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
-    p.tail_idx = a.tails + off * a.ts; p.tail_stride = a.ts;
-  }
-  p.part_g = w.part_g; p.slots_g = on[IT_G_L2] ? (c->dims.embed_dim + 31) / 32 : 0;  // only the valid columns
-  p.w3 = c->d_w3_pad; p.b3 = c->d_b3;
-  p.logits = a.logits ? a.logits + off : nullptr;
-  p.probs = a.probs ? a.probs + off : nullptr;
-  p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
-  p.trace = c->trace;
-  const int grid = pass_grid(c);  // phase 0 and the item order assume this many co-resident CTAs
-  { LaunchScope ls(c, PBG_K_PASS, a.stream);
-    pbg_pass_kernel<<<grid, kPassThreads, PassSmem::kTotal, a.stream>>>(p); }
-  PBG_CUDA(c, cudaGetLastError());
-  return PBG_OK;
-}
 
 template <bool TR, bool FASTG, bool BIASS>
 cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s, bool pdl) {
@@ -782,7 +664,6 @@ int pbg_set_launch_width(pbg_ctx* c, int n_ctas) {
   if (!c) return PBG_ERR_INVALID;
   if (n_ctas < 0) return fail(c, PBG_ERR_INVALID, "launch width must be >= 0");
   c->launch_ctas = n_ctas;
-  c->item_cache.clear();  // the single-CTA kernel's cached tiling plans depend on the grid
   return PBG_OK;
 }
 

@@ -22,7 +22,7 @@
 #include <cuda.h>
 #include "ptx.cuh"
 #include "gemm_tc.cuh"
-#include "pass_kernel.cuh"
+#include "pass_common.cuh"
 
 namespace pbg {
 
