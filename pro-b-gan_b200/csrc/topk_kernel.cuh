@@ -256,24 +256,30 @@ pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
             const int pb = tsb | (g << 5);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              int k = (max(static_cast<int>(cur[j]), 0) & ~0xFFF) | (pb | j);
-              int tt;
-              tt = max(m1, k); k = min(m1, k); m1 = tt;
-              tt = max(m2, k); k = min(m2, k); m2 = tt;
-              tt = max(m3, k); k = min(m3, k); m3 = tt;
-              tt = max(m4, k); k = min(m4, k); m4 = tt;
-              tt = max(m5, k); k = min(m5, k); m5 = tt;
-              m6 = max(m6, k);
+              const int k = (max(static_cast<int>(cur[j]), 0) & ~0xFFF) | (pb | j);
+              // sorted insert, every level from the OLD values (depth 2 instead of a 11-deep dependent chain):
+              // new m_i = max(m_i, min(m_{i-1}, k))
+              const int n6 = max(m6, min(m5, k)), n5 = max(m5, min(m4, k)), n4 = max(m4, min(m3, k));
+              const int n3 = max(m3, min(m2, k)), n2 = max(m2, min(m1, k)), n1 = max(m1, k);
+              m1 = n1; m2 = n2; m3 = n3; m4 = n4; m5 = n5; m6 = n6;
             }
           } else {
+            // four scores per warp vote: the control flow around a vote costs more than the compares
             const int e0 = ent0 + g * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float sv = __uint_as_float(cur[j]);
-              const bool pass = sv > tau;
-              if (__any_sync(0xffffffffu, pass)) {
-                const unsigned long long r = tk_pass(lsc, lix, lane, pass && e0 + j < p.N, sv, e0 + j, cnt, tau);
-                cnt = static_cast<int>(r >> 32); tau = __uint_as_float(static_cast<unsigned>(r));
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              const float s0 = __uint_as_float(cur[j4]), s1 = __uint_as_float(cur[j4 + 1]);
+              const float s2 = __uint_as_float(cur[j4 + 2]), s3 = __uint_as_float(cur[j4 + 3]);
+              if (__any_sync(0xffffffffu, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > tau)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float sv = __uint_as_float(cur[j4 + u]);
+                  const bool pass = sv > tau;
+                  if (__any_sync(0xffffffffu, pass)) {
+                    const unsigned long long r = tk_pass(lsc, lix, lane, pass && e0 + j4 + u < p.N, sv, e0 + j4 + u, cnt, tau);
+                    cnt = static_cast<int>(r >> 32); tau = __uint_as_float(static_cast<unsigned>(r));
+                  }
+                }
               }
             }
           }
