@@ -37,6 +37,7 @@ from pbg import launcher, synth  # noqa: E402
 REFERENCE_SCRIPT = "/root/reference/pro_b_gan_infer.py"
 B = 16
 TOP_K = 10
+ANALYZE_HEADS, ANALYZE_TAILS = [3, 40000, 65535], [17, 1234]
 
 
 def run_cli(argv, ckpt_path):
@@ -65,6 +66,17 @@ def main():
     (HERE / "config1_score_triplets.json").write_text(json.dumps(score, indent=1))
     (HERE / "config1_predict_tails.json").write_text(json.dumps(pred, indent=1))
     (HERE / "config1_model_info.json").write_text(json.dumps(info, indent=1))
+
+    # analyze_relations is accepted by the CLI but never dispatched (a quirk the tests preserve), so the method of
+    # the unmodified class is called directly: 3 heads x 2 tails x all 64 relations, top 5        -> :264-318
+    with tempfile.TemporaryDirectory() as d2:
+        path2 = str(Path(d2) / "synthetic_ckpt.pt")
+        torch.save(ckpt, path2)
+        ref = launcher.load_reference_script(REFERENCE_SCRIPT, model_module=oracle)
+        with contextlib.redirect_stdout(io.StringIO()):
+            inf = ref.ProtBGANInference(path2, "cpu")
+            rel = inf.analyze_relations(ANALYZE_HEADS, ANALYZE_TAILS, top_k=5)
+    (HERE / "config1_analyze_relations.json").write_text(json.dumps(rel, indent=1))
 
     # direct tensors, B = 16
     G, D = synth.make_models(oracle.ModularGenerator, oracle.ModularDiscriminator)
