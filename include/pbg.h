@@ -202,6 +202,14 @@ int pbg_set_result_mirrors(pbg_ctx* ctx, int n, void* const* gen_out, float* con
 int pbg_topk_prepare(pbg_ctx* ctx, const float* table, int64_t N, void* stream);
 int pbg_topk(pbg_ctx* ctx, const float* queries, int64_t B, int k, int64_t* out_idx, float* out_scores, void* stream);
 
+/* Host-side ingest of the CLI's index arrays; replaces json.loads (pro_b_gan_infer.py:485 --input_pairs, :493
+ * --input_triplets, :501 --input_entities) + torch.tensor(list) (:135-136, :182, :226).  `text[0..len)` is the JSON
+ * text: "[a, b, ...]" for cols == 1, "[[a, b], ...]" / "[[h, r, t], ...]" for cols == 2 / 3 (1 <= cols <= 8).  Ids are
+ * JSON integers that fit int64; a float, a ragged row or any other token is PBG_ERR_INVALID with the byte offset in
+ * pbg_last_error(NULL).  Writes at most cap_rows rows of `cols` int64 to `out` (out may be NULL to count) and
+ * returns the number of rows in the text (>= 0), or -PBG_ERR_INVALID.  No ctx, no device, thread-safe. */
+int64_t pbg_parse_index_rows(const char* text, size_t len, int cols, int64_t* out, size_t cap_rows);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const GatherParams p
     bool bad = false;
     if (p.heads != nullptr) {
       long long i = p.heads[b * p.head_stride];
+      if (i < 0) i += p.N;  // node_emb[idx] is tensor indexing: -N..-1 count from the end (pro_b_gan_infer.py:139)
       if (i < 0 || i >= p.N) { bad = true; i = 0; }
       hrow = p.node_emb + i * p.E;
     } else {
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const GatherParams p
     if (xd != nullptr) {
       if (p.tails != nullptr) {
         long long i = p.tails[b * p.tail_stride];
+        if (i < 0) i += p.N;
         if (i < 0 || i >= p.N) { bad = true; i = 0; }
         trow = p.node_emb + i * p.E;
       } else {

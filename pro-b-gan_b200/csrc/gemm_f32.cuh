@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) cosine_f32_kernel(const float* __restrict
   const long long num_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long m = warp_global; m < M; m += num_warps) {
     long long t = tails[m * tail_stride];
+    if (t < 0) t += n_ent;  // same wrap as the gather
     t = (t < 0 || t >= n_ent) ? 0 : t;
     const float* prow = pred + m * ldp;
     const float* trow = node_emb + t * E;

@@ -226,13 +226,13 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
     const int which = lane % 3;
     if (row < g.B) {
       if (which == 0) {
-        if (g.heads) { long long i = g.heads[row * g.head_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        if (g.heads) { long long i = g.heads[row * g.head_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
         else src = g.h + row * g.E;
       } else if (which == 1) {
         if (g.rels) { long long i = g.rels[row * g.rel_stride]; if (i < 0 || i >= g.R) { bad = true; i = 0; } src = g.rel_emb + i * g.E; }
         else src = g.r + row * g.E;
       } else if (xd != nullptr) {
-        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
         else src = g.t + row * g.E;
       }
     }
@@ -582,6 +582,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const float* trow = nullptr;
         if (row_ok) {
           long long tid = p.tail_idx[grow * p.tail_stride];
+          if (tid < 0) tid += p.n_ent;                  // same wrap as the gather
           tid = (tid < 0 || tid >= p.n_ent) ? 0 : tid;  // the gather has already flagged it
           trow = p.tail_tab + tid * p.n_valid;
         }

@@ -92,13 +92,13 @@ __device__ __forceinline__ void pass_gather_group(const GatherParams& g, long lo
     const int which = lane % 3;
     if (row < g.B) {
       if (which == 0) {
-        if (g.heads) { long long i = g.heads[row * g.head_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        if (g.heads) { long long i = g.heads[row * g.head_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
         else src = g.h + row * g.E;
       } else if (which == 1) {
         if (g.rels) { long long i = g.rels[row * g.rel_stride]; if (i < 0 || i >= g.R) { bad = true; i = 0; } src = g.rel_emb + i * g.E; }
         else src = g.r + row * g.E;
       } else if (xd != nullptr) {
-        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
+        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
         else src = g.t + row * g.E;
       }
     }

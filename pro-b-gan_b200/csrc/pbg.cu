@@ -29,6 +29,7 @@
 #include "pass_common.cuh"
 #include "pass2_kernel.cuh"
 #include "topk_kernel.cuh"
+#include "index_rows.cuh"
 
 using namespace pbg;
 
@@ -534,6 +535,15 @@ int pbg_abi_version(void) { return PBG_ABI_VERSION; }
 const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t pbg_parse_index_rows(const char* text, size_t len, int cols, int64_t* out, size_t cap_rows) {
+  if (!text || cols < 1 || cols > 8) return -(int64_t)fail(nullptr, PBG_ERR_INVALID, "parse_index_rows: null text or cols outside 1..8");
+  const char* msg = nullptr;
+  size_t off = 0;
+  const long long rows = pbg_host::parse_index_rows(text, len, cols, out, cap_rows, &msg, &off);
+  if (rows < 0) return -(int64_t)fail(nullptr, PBG_ERR_INVALID, "parse_index_rows: %s at byte %zu", msg, off);
+  return rows;
+}
 
 int pbg_topk_prepare(pbg_ctx* c, const float* table, int64_t N, void* stream) {
   if (!c) return PBG_ERR_INVALID;

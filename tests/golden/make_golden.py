@@ -37,6 +37,7 @@ from pbg import launcher, synth  # noqa: E402
 REFERENCE_SCRIPT = "/root/reference/pro_b_gan_infer.py"
 B = 16
 TOP_K = 10
+SIMILAR_QUERIES = [0, 7, 40000, 65535]
 ANALYZE_HEADS, ANALYZE_TAILS = [3, 40000, 65535], [17, 1234]
 
 
@@ -63,9 +64,13 @@ def main():
         score = run_cli(["--task", "score_triplets", "--input_triplets", json.dumps(triplets)], path)
         pred = run_cli(["--task", "predict_tails", "--input_pairs", json.dumps(pairs), "--top_k", str(TOP_K)], path)
         info = run_cli(["--task", "model_info"], path)
+        similar = run_cli(["--task", "similar_entities", "--input_entities", json.dumps(SIMILAR_QUERIES), "--top_k",
+                           str(TOP_K)], path)
     (HERE / "config1_score_triplets.json").write_text(json.dumps(score, indent=1))
     (HERE / "config1_predict_tails.json").write_text(json.dumps(pred, indent=1))
+    info["checkpoint_path"] = "synthetic_ckpt.pt"   # the temp directory differs per run
     (HERE / "config1_model_info.json").write_text(json.dumps(info, indent=1))
+    (HERE / "config1_similar_entities.json").write_text(json.dumps(similar, indent=1))
 
     # analyze_relations is accepted by the CLI but never dispatched (a quirk the tests preserve), so the method of
     # the unmodified class is called directly: 3 heads x 2 tails x all 64 relations, top 5        -> :264-318
