@@ -519,7 +519,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     const int wep = warp - 2;          // 0..7
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int half = wep >> 2;         // which half of a tile's 64-column chunks this warp takes
-    uint8_t* st = smem + L::kStagingOff + wep * L::kStagingPerWarp;
+    // staging tile of warp (q, half): tiles of one lane quarter are adjacent, so that its two warps can lay whole output
+    // rows (both column halves) out contiguously for the mirror stores of the last generator layer
+    uint8_t* st = smem + L::kStagingOff + (q * 2 + half) * L::kStagingPerWarp;
     uint32_t acc = 0, acc_phase = 0, slot = 0, sphase = 0;
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
@@ -789,12 +791,14 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             p2_tail_dot(st, f, col0, p.n_valid, lane, cs_dot, cs_pp, cs_tt);
             p2_tail_stage(st, tv2, lane);
             p2_tail_dot(st, f + 32, col0 + 32, p.n_valid, lane, cs_dot, cs_pp, cs_tt);
+            if (tpt) tr[245] = clock64();
             if (in_cta) {
               // the two warps of this lane quarter hold the row's two halves: the upper one hands its sums over
               // through shared memory, the lower one finishes (fixed order: columns 0..63 + columns 64..127)
               float* xq = xchg + (q * 32 + lane) * 3;
               if (half == 1) { xq[0] = cs_dot; xq[1] = cs_pp; xq[2] = cs_tt; }
               asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+              if (tpt) tr[255] = clock64();
               if (half == 0) {
                 const float d = cs_dot + xq[0], pp = cs_pp + xq[1], tt = cs_tt + xq[2];
                 // F.cosine_similarity(pred, t, dim=1), eps = 1e-8 on each norm (pro_b_gan_infer.py:202)
@@ -813,12 +817,18 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             }
           }
           if (tpt) tr[235] = clock64();
-          if (want_out && row_ok) {
+          // Common case (bf16 rows of 128 columns: this quarter's two warps hold 32 whole, consecutive rows): the rows
+          // are laid out in the two warps' staging tiles and leave as ONE 8 KB bulk store to the caller's buffer and
+          // one per mirror.  Otherwise: 16-byte stores from registers to the caller's buffer, and for mirrors (peer
+          // GPUs over NVLink, where 16-byte stores would cross the link as 16-byte packets) one 128-byte bulk store
+          // per lane and mirror.
+          const bool bulk_mirror = p.n_mirror > 0 && (p.n_valid & 63) == 0;
+          const bool pair_out = want_out && in_cta && !p.out_f32 && p.n_valid == 128 && p.ld_gen == 128;
+          if (want_out && row_ok && !pair_out) {
             // one row per lane, 16-byte stores (2 MB for a 4096-row pass: not worth a transpose through shared memory)
             // the caller's own buffer: 16-byte stores straight from registers; mirrors (peer GPUs over NVLink): the row
             // segment goes through this lane's 128 bytes of the staging tile and out as one 128-byte bulk store per
             // mirror -- 16-byte stores would cross NVLink as 16-byte packets
-            const bool bulk_mirror = p.n_mirror > 0 && (p.n_valid & 63) == 0;
             for (int mi = -1; mi < (bulk_mirror ? 0 : p.n_mirror); ++mi) {
               void* base = mi < 0 ? p.gen_out : p.mir_gen[mi];
               if (p.out_f32) {
@@ -869,7 +879,34 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
               }
             }
           }
-          if (want_out && p.n_mirror > 0) {   // (warp-uniform) the staging tile is free again when every lane's stores have read it
+          if (pair_out) {                     // (uniform over the quarter's two warps)
+            uint8_t* region = smem + L::kStagingOff + q * 2 * L::kStagingPerWarp;   // both warps' tiles: 32 rows x 256 B
+            asm volatile("bar.sync %0, 64;" ::"r"(5 + q) : "memory");   // both warps are done with their own tiles
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              uint4 w;
+              w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
+              w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
+              w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
+              w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
+              *reinterpret_cast<uint4*>(region + lane * 256 + half * 128 + t * 16) = w;
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 64;" ::"r"(5 + q) : "memory");   // the rows are complete
+            if (half == 0 && lane == 0) {
+              const long long row0 = grow - lane;
+              const long long nrows = min(32ll, p.M - row0);
+              if (nrows > 0) {
+                bulk_store_1d(static_cast<char*>(p.gen_out) + row0 * 256, region, static_cast<uint32_t>(nrows * 256));
+                for (int mi = 0; mi < p.n_mirror; ++mi)
+                  bulk_store_1d(static_cast<char*>(p.mir_gen[mi]) + row0 * 256, region, static_cast<uint32_t>(nrows * 256));
+                tma_store_commit();
+                tma_store_wait_read<0>();
+              }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(5 + q) : "memory");   // the tiles may be reused
+          }
+          if (want_out && p.n_mirror > 0 && !pair_out) {   // (warp-uniform) the staging tile is free again when every lane's stores have read it
             tma_store_wait_read<0>();
             __syncwarp();
           }
@@ -913,7 +950,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       tr[7] = w_acc; tr[8] = clock64(); tr[10] = busy;
       tr[240] = ph_ld; tr[241] = ph_math; tr[242] = ph_st; tr[243] = ph_n; tr[244] = ph_wr;
       tr[251] = ph_m1; tr[252] = ph_w2;
-      tr[245] = 0; tr[246] = pf_wait; tr[247] = pf_total; tr[248] = pf_n;
+      tr[246] = pf_wait; tr[247] = pf_total; tr[248] = pf_n;
     }
   }
 

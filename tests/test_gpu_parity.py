@@ -354,20 +354,23 @@ def test_passes_on_concurrent_lanes_match_sequential(cuda_models, dev_tables, sy
             assert torch.equal(got[i][k], ref[i][k]), f"step {i}: {k} differs"
 
 
-def test_result_mirrors_receive_the_same_rows(cuda_models, dev_tables, synth, dev):
-    """pbg_set_result_mirrors with two mirror buffers (same device here; peers' windows in a multi-GPU job)."""
+@pytest.mark.parametrize("B", [1000, 4096, 31])
+def test_result_mirrors_receive_the_same_rows(cuda_models, dev_tables, synth, dev, B):
+    """pbg_set_result_mirrors with two mirror buffers (same device here; peers' windows in a multi-GPU job).  The
+    buffers carry 64 guard rows behind the batch: the bulk stores of a ragged last row group must not touch them."""
     import modular_prot_b_gan as m
-    B, E = 1000, 128
+    E, G = 128, 64
     eng = m.make_fused_engine(*cuda_models)
     trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
-    mir = [{"gen_out": torch.zeros(B, E, dtype=torch.bfloat16, device=dev), "gen_scores": torch.zeros(B, device=dev),
-            "logits": torch.zeros(B, device=dev), "probs": torch.zeros(B, device=dev)} for _ in range(2)]
+    mir = [{"gen_out": torch.full((B + G, E), 7.0, dtype=torch.bfloat16, device=dev), "gen_scores": torch.full((B + G,), 7.0, device=dev),
+            "logits": torch.full((B + G,), 7.0, device=dev), "probs": torch.full((B + G,), 7.0, device=dev)} for _ in range(2)]
     eng.set_result_mirrors(**{k: [d[k].data_ptr() for d in mir] for k in mir[0]})
     res = _pass(eng, dev_tables, trip, z)
     torch.cuda.synchronize()
     for d in mir:
         for k in d:
-            assert torch.equal(d[k], res[k]), f"mirror {k} differs"
+            assert torch.equal(d[k][:B], res[k]), f"mirror {k} differs"
+            assert bool((d[k][B:] == 7.0).all()), f"mirror {k}: rows behind the batch were written"
     with pytest.raises(Exception):   # mirrors are a bf16-mode feature: the fp32 path must refuse, not ignore them
         eng.score_triplets(*dev_tables, trip, z, want_gen_out=True, precision="fp32")
     eng.set_result_mirrors()

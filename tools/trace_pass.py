@@ -75,7 +75,8 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     if tsel.any():
         tt = t[tsel]
         P(f"   TANH epilogue (warp 2, last tile): start -> tmem loaded {(tt[:, 233] - tt[:, 232]).mean():.0f}  tanh {(tt[:, 234] - tt[:, 233]).mean():.0f}"
-          f"  cosine {(tt[:, 235] - tt[:, 234]).mean():.0f}  output {(tt[:, 236] - tt[:, 235]).mean():.0f}")
+          f"  cosine {(tt[:, 235] - tt[:, 234]).mean():.0f} (tail dots {(tt[:, 245] - tt[:, 234]).mean():.0f}, partner wait {(tt[:, 255] - tt[:, 245]).mean():.0f},"
+          f" finish + store {(tt[:, 235] - tt[:, 255]).mean():.0f})  output {(tt[:, 236] - tt[:, 235]).mean():.0f}")
     pfn = ph[:, 8].clamp_min(1)
     P(f"   tile hand-off (warp 2, clk per tile): bulk-store completion wait {(ph[:, 6] / pfn).mean():.0f}  whole arrival {(ph[:, 7] / pfn).mean():.0f}")
     gsel = ph[:, 9] > 0
