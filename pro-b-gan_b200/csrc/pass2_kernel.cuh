@@ -57,7 +57,9 @@ struct P2Layer {
   __nv_bfloat16* out;// PEPI_STORE: next layer's A operand
 };
 
-struct P2Segment { int kind, n_tiles, start, rb0; };  // static tickets from `start` up to the next segment: (kind, n = i % n_tiles, rb = rb0 + i / n_tiles)
+// Static tickets from `start` up to the next segment.  Per row block rb = rb0 + i / (n_tiles + n_tiles2) the segment
+// holds the n_tiles tiles of layer `kind` followed by the n_tiles2 tiles of layer `kind2` (n_tiles2 = 0: one layer).
+struct P2Segment { int kind, n_tiles, start, rb0, kind2, n_tiles2; };
 
 struct alignas(64) Pass2Params {
   CUtensorMap tm_a[5];  // A operand of layer i: xg0, xd0, actG0, actD0, actG1   (box 64 x 128 rows, SWIZZLE_128B)
@@ -397,8 +399,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           int sg = 0;
           while (sg + 1 < p.n_seg && ticket >= p.seg[sg + 1].start) ++sg;
           const int i = ticket - p.seg[sg].start;
-          const int nt = p.seg[sg].n_tiles;
-          it = make_uint2(static_cast<uint32_t>(p.seg[sg].kind) | (static_cast<uint32_t>(i % nt) << 8),
+          const int nt1 = p.seg[sg].n_tiles, nt = nt1 + p.seg[sg].n_tiles2;
+          const int j = i % nt;
+          it = make_uint2(static_cast<uint32_t>(j < nt1 ? p.seg[sg].kind : p.seg[sg].kind2) | (static_cast<uint32_t>(j < nt1 ? j : j - nt1) << 8),
                           static_cast<uint32_t>(p.seg[sg].rb0 + i / nt));
         }
         // Ring protocol: the item lives in this (the scheduler's) CTA only; the leader's consumers fetch it with a
@@ -406,6 +409,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         // release is a MEMBAR.ALL.GPU in front of every arrive): the slot is written to local shared memory before
         // the remote arrive leaves this SM, and a consumer's arrive on sched_empty carries a data dependency on its
         // load of the slot.
+        // The scheduler, not the producer, waits for the item's A operand (the row block of the previous layer, or the
+        // gathered rows): it runs up to a ring ahead of the workers, so the wait costs nothing in steady state, every
+        // item in the ring is ready, and the producers refill each stage with W and A the moment it frees.  (A
+        // producer that polls between an item's loads delays the A loads of the first ring's worth of K-blocks until
+        // the previous item's LAST stage has freed, and its proxy fence then waits for its own bulk loads in flight:
+        // 3-4 thousand clocks of tensor-pipe idle per tile boundary, tools/ubench_pipe.cu vs the r1f trace.)
+        if ((it.x & 0xff) != IT_END) p2_poll_dep(p, p.layer[it.x & 0xff].dep_kind, static_cast<int>(it.y));
         mbar_wait(&sched_empty[slot], sphase ^ 1);
         ring[slot] = it;
         mbar_arrive(&sched_full[slot]);
@@ -438,28 +448,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const uint32_t bytes_pair = 2u * (L::kA + static_cast<uint32_t>(w_rows) * kBlockK * 2);
         const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
         const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
-        // the item's W tiles do not depend on anything: put the first ring's worth in flight, then wait for the A
-        // operand's row block, then issue the matching A loads
-        const int npre = min(ly.num_kb, kP2Stages);
-        {
-          uint32_t st2 = stage, ph2 = phase;
-          for (int kb = 0; kb < npre; ++kb) {
-            if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[st2], ph2 ^ 1); w_empty += clock64() - t; }
-            else mbar_wait(&empty_bar[st2], ph2 ^ 1);
-            if (leader) mbar_arrive_expect_tx(&full_bar[st2], bytes_pair);
-            tma_load_2d_pair(smem + st2 * L::kStage + L::kA, &p.tm_w[kind], lead_full + st2 * 8, kb * kBlockK, w_row);
-            if (++st2 == kP2Stages) { st2 = 0; ph2 ^= 1; }
-          }
-        }
-        { const long long t = tr ? clock64() : 0;
-          p2_poll_dep(p, ly.dep_kind, rb);
-          if (tr) { w_dep += clock64() - t; if (ti) ti[1] = clock64(); } }
-        for (int kb = 0; kb < npre; ++kb) {
-          if (tr) t_issue[stage] = clock64();
-          tma_load_2d_pair(smem + stage * L::kStage, &p.tm_a[kind], lead_full + stage * 8, kb * kBlockK, a_row);
-          if (++stage == kP2Stages) { stage = 0; phase ^= 1; }
-        }
-        for (int kb = npre; kb < ly.num_kb; ++kb) {
+        if (ti) ti[1] = clock64();
+        for (int kb = 0; kb < ly.num_kb; ++kb) {
           if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
           else mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStage;

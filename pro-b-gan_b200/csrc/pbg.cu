@@ -436,19 +436,32 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     // then L1 of every wave, then L2).  One wave measured best at every size (PBG_WAVES to experiment).
     static const int waves_env = [] { const char* e = getenv("PBG_WAVES"); return e ? atoi(e) : 1; }();
     const int waves = std::max(1, std::min(waves_env, std::min(nrb, 3)));
-    static const int phase_kinds[3][2] = {{IT_G_L0, IT_D_L0}, {IT_G_L1, IT_D_L1}, {IT_G_L2, -1}};
+    // Ticket order (a topological order of the layer graph): L0 of both models, the generator's L1, then per row
+    // block the discriminator's L1 tiles followed by the generator's L2 tile.  The last generator layer is
+    // epilogue-bound (tanh, cosine, output rows: ~3x a STORE epilogue for a quarter of the MMA time) and D's L1 is
+    // MMA-bound, so a pair that draws both kinds keeps its tensor pipe and its epilogue warps busy; all of G's L2
+    // at the very end leaves the tensor pipes idle for the whole tail of the pass (PBG_MIX=0: the old order).
+    static const int mix_env = [] { const char* e = getenv("PBG_MIX"); return e ? atoi(e) : 1; }();
+    const bool mix = on[IT_D_L1] && on[IT_G_L2] && mix_env != 0;
     int start = 0;
-    for (int ph = 0; ph < 3; ++ph) {
-      for (int wv = 0; wv < waves; ++wv) {
-        const int rb_lo = static_cast<int>(static_cast<long long>(nrb) * wv / waves);
-        const int rb_hi = static_cast<int>(static_cast<long long>(nrb) * (wv + 1) / waves);
-        for (int j = 0; j < 2; ++j) {
-          const int k = phase_kinds[ph][j];
-          if (k < 0 || !on[k] || rb_hi == rb_lo) continue;
-          p.seg[p.n_seg++] = P2Segment{k, p.layer[k].n_tiles, start, rb_lo};
-          start += (rb_hi - rb_lo) * p.layer[k].n_tiles;
-        }
-      }
+    auto add_seg = [&](int k, int rb_lo, int rb_hi, int k2 = -1) {
+      if (k < 0 || !on[k] || rb_hi == rb_lo) return;
+      const int nt2 = (k2 >= 0 && on[k2]) ? p.layer[k2].n_tiles : 0;
+      p.seg[p.n_seg++] = P2Segment{k, p.layer[k].n_tiles, start, rb_lo, nt2 ? k2 : k, nt2};
+      start += (rb_hi - rb_lo) * (p.layer[k].n_tiles + nt2);
+    };
+    for (int wv = 0; wv < waves; ++wv) {
+      const int rb_lo = static_cast<int>(static_cast<long long>(nrb) * wv / waves);
+      const int rb_hi = static_cast<int>(static_cast<long long>(nrb) * (wv + 1) / waves);
+      add_seg(IT_G_L0, rb_lo, rb_hi);
+      add_seg(IT_D_L0, rb_lo, rb_hi);
+    }
+    add_seg(IT_G_L1, 0, nrb);
+    if (mix) {
+      add_seg(IT_D_L1, 0, nrb, IT_G_L2);
+    } else {
+      add_seg(IT_D_L1, 0, nrb);
+      add_seg(IT_G_L2, 0, nrb);
     }
     if (start != total) return fail(c, PBG_ERR_INVALID, "internal: static item list does not cover the pass");
     p.n_total = start;

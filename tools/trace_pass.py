@@ -20,7 +20,9 @@ def P(*a):
 
 dev = torch.device("cuda:0")
 G, D = synth.make_models(m.ModularGenerator, m.ModularDiscriminator)
-eng = m.make_fused_engine(G.to(dev), D.to(dev))
+import os
+CTAS = int(os.environ.get("TRACE_CTAS", "0"))   # SMs per pass (0 = all), e.g. 48 = bench.py's lane width
+eng = m.make_fused_engine(G.to(dev), D.to(dev), ctas=CTAS)
 node_emb, rel_w = (t.to(dev) for t in synth.make_tables())
 for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     trip, z = synth.make_triplets(B).to(dev), synth.make_latents(B).to(dev)
@@ -53,7 +55,7 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     hdr, items = t[:, :16], t[:, 16:240].reshape(t.shape[0], 56, 4)
     raw0 = ti64[:, 16:240].reshape(t.shape[0], 56, 4)[:, :, 0]
     c0 = hdr[:, 0:1]
-    P(f"pass B={B}: {us:.2f} us/step (graph of {n}) = {B / us:.1f} M samples/s = {B * 4850688 / us / 1e6:.0f} TFLOP/s; {t.shape[0]} CTAs")
+    P(f"pass B={B} on {CTAS or 'all'} SMs: {us:.2f} us/step (graph of {n}) = {B / us:.1f} M samples/s = {B * 4850688 / us / 1e6:.0f} TFLOP/s; {t.shape[0]} CTAs")
     P(f"   CTA lifetime (begin -> epilogue end): mean {(hdr[:, 8] - hdr[:, 0]).mean():.0f} max {(hdr[:, 8] - hdr[:, 0]).max():.0f} clk;"
       f"  begin skew (globaltimer) {(hdr[:, 14].max() - hdr[:, 14].min()):.0f} ns")
     P(f"   per CTA: items {hdr[:, 12].mean():.1f}  k-blocks {hdr[:, 9].mean():.1f} (max {hdr[:, 9].max():.0f})  -> MMA floor {hdr[:, 9].mean() * 512:.0f} clk")
@@ -99,7 +101,7 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
         P(f"   {name}: n={int(sel.sum()):5d} claim@ {cl.mean():8.0f} (min {cl.min():.0f} max {cl.max():.0f})  dep-wait {depw.mean():7.0f} (max {depw.max():.0f})"
           f"  claim->acc {((accr - c0s) - cl).mean():7.0f}  epilogue {(done - accr).mean():6.0f} (max {(done - accr).max():.0f})  done@ max {(done - c0s).max():.0f}")
     if B <= 4096:
-        for cta in (0, 60, 140):
+        for cta in (0, 20, 46) if CTAS else (0, 60, 140):
             if cta >= t.shape[0]:
                 continue
             rows = []
