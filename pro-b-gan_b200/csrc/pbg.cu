@@ -436,12 +436,11 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     // then L1 of every wave, then L2).  One wave measured best at every size (PBG_WAVES to experiment).
     static const int waves_env = [] { const char* e = getenv("PBG_WAVES"); return e ? atoi(e) : 1; }();
     const int waves = std::max(1, std::min(waves_env, std::min(nrb, 3)));
-    // Ticket order (a topological order of the layer graph): L0 of both models, the generator's L1, then per row
-    // block the discriminator's L1 tiles followed by the generator's L2 tile.  The last generator layer is
-    // epilogue-bound (tanh, cosine, output rows: ~3x a STORE epilogue for a quarter of the MMA time) and D's L1 is
-    // MMA-bound, so a pair that draws both kinds keeps its tensor pipe and its epilogue warps busy; all of G's L2
-    // at the very end leaves the tensor pipes idle for the whole tail of the pass (PBG_MIX=0: the old order).
-    static const int mix_env = [] { const char* e = getenv("PBG_MIX"); return e ? atoi(e) : 1; }();
+    // Ticket order (a topological order of the layer graph): L0 of both models, then L1 of both, then the generator's
+    // L2.  PBG_MIX=1 instead interleaves, per row block, the discriminator's L1 tiles (MMA-bound) with the generator's
+    // L2 tile (epilogue-bound: tanh, cosine, output rows); measured on B200 it changes nothing at 6 lanes x 48 SMs
+    // (196.5 vs 197.0 M samples/s) or at B = 32768 (167.9 vs 167.1 us) and costs a single 48-SM pass 8 % -- off.
+    static const int mix_env = [] { const char* e = getenv("PBG_MIX"); return e ? atoi(e) : 0; }();
     const bool mix = on[IT_D_L1] && on[IT_G_L2] && mix_env != 0;
     int start = 0;
     auto add_seg = [&](int k, int rb_lo, int rb_hi, int k2 = -1) {
