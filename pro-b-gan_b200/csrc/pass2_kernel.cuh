@@ -216,8 +216,13 @@ __device__ __forceinline__ void p2_tail_dot(const uint8_t* st, const float* f, i
 
 // Gather group for the common layout (E = 128, Z <= 128, unpadded xg / xd rows): four rows through the warp's staging
 // tile and out with bulk stores, so that the arrival can follow cp.async.bulk.wait_group (a few hundred clocks)
-// instead of a release fence over 28 generic stores per lane.  Returns after the stores have completed.
-__device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long long group, int lane, uint8_t* st) {
+// instead of a release fence over 28 generic stores per lane.  Returns with lane 0's last bulk store committed but
+// not waited for: the caller completes it (wait_group 0, then the arrival) -- `before_staging()` is called once this
+// group's row loads are in flight and before the staging tile is written, which is where the caller completes the
+// PREVIOUS group, so that a store's completion latency hides behind the next group's load latency.
+template <class F>
+__device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long long group, int lane, uint8_t* st,
+                                                     F&& before_staging) {
   const long long r0 = group * 4;
   __nv_bfloat16* xg = static_cast<__nv_bfloat16*>(g.xg);
   __nv_bfloat16* xd = static_cast<__nv_bfloat16*>(g.xd);
@@ -258,6 +263,7 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
       if (xg != nullptr && lane < Z4) zv[j] = ld_stream4(g.z + row * g.Z + 4 * lane);
     }
   }
+  before_staging();
   const long long nrow = min(4ll, g.B - r0);   // rows of a group are consecutive in xg / xd: one bulk store each
   // the staging tile holds one of the two outputs at a time (4 x 640 B, then 4 x 768 B)
   if (xg != nullptr) {
@@ -292,8 +298,6 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
       tma_store_commit();
     }
   }
-  if (lane == 0) tma_store_wait<0>();
-  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -522,6 +526,14 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     // would otherwise wait -- for a ring item, for an accumulator -- so only the first groups sit in front of the
     // first tiles; the counter hands the groups out in row order, which is the order the tiles need them in.
     bool more_groups = true;
+    int pend_rb = -1;   // FASTG: row block of the group whose bulk stores are committed but not yet waited for
+    auto gather_flush = [&]() {
+      if (pend_rb >= 0) {
+        if (lane == 0) { tma_store_wait<0>(); red_relaxed_gpu_add(p.ready + DEP_X * p.rb_cap + pend_rb, 1); }
+        __syncwarp();
+        pend_rb = -1;
+      }
+    };
     auto gather_one = [&]() {   // warp-uniform; false once every group has been claimed
       int g = 0;
       if (lane == 0) g = atomicAdd(&p.sched->p0_next, 1);
@@ -529,9 +541,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (g >= p.phase0_groups) { more_groups = false; return; }
       if (tr && threadIdx.x == 64) tr[249] = clock64();
       if (FASTG) {
-        p2_gather_group_bulk(p.gather, g, lane, st);   // returns with the rows in global memory
+        p2_gather_group_bulk(p.gather, g, lane, st, gather_flush);
         if (tr && threadIdx.x == 64) tr[250] = clock64();
-        p2_arrive_done(p, DEP_X, g / kP2GroupsPerBlock, lane);
+        pend_rb = static_cast<int>(g / kP2GroupsPerBlock);   // completed by the next group, or by gather_flush()
       } else {
         pass_gather_group<2>(p.gather, g, lane);
         if (tr && threadIdx.x == 64) tr[250] = clock64();
@@ -539,10 +551,12 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       }
     };
     gather_one();   // everybody starts with one group: nothing else can be ready yet
+    gather_flush(); // ... and the first tiles wait for exactly these groups: no deferral for the first round
     bool bias_ok = !BIASS;
     long long pf_wait = 0, pf_total = 0, pf_n = 0;
     for (;;) {
       while (more_groups && !__all_sync(0xffffffffu, mbar_test_wait(&sched_full[slot], sphase))) gather_one();
+      gather_flush();   // nothing may block, or touch the staging tile, with a group's arrival still owed
       mbar_wait(&sched_full[slot], sphase);
       const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
       __syncwarp();
@@ -552,6 +566,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (kind == IT_END) break;
       // idle until this item's accumulator is ready: gather (the staging tile is free between tiles)
       while (more_groups && !__all_sync(0xffffffffu, mbar_test_wait(&tmem_full[acc], acc_phase))) gather_one();
+      gather_flush();
       if (tr && threadIdx.x == 64 && tr[5] == 0) tr[5] = clock64();
       if (!bias_ok) { mbar_wait(bias_bar, 0); bias_ok = true; }  // the bias bulk copies issued in the prologue have landed
       const int n_blk = (it.x >> 8) & 0xff;
