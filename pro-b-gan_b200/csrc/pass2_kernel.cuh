@@ -68,6 +68,7 @@ struct alignas(64) Pass2Params {
   P2Layer layer[5];
   GatherParams gather;
   unsigned layer_mask;
+  int gather_defer;      // 1: a gather group's completion wait + arrival ride behind the next group's loads
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
   int n_total;          // tickets of this launch
@@ -544,6 +545,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         p2_gather_group_bulk(p.gather, g, lane, st, gather_flush);
         if (tr && threadIdx.x == 64) tr[250] = clock64();
         pend_rb = static_cast<int>(g / kP2GroupsPerBlock);   // completed by the next group, or by gather_flush()
+        if (!p.gather_defer) gather_flush();                 // PBG_GATHER_DEFER=0: complete every group at once
       } else {
         pass_gather_group<2>(p.gather, g, lane);
         if (tr && threadIdx.x == 64) tr[250] = clock64();

@@ -468,6 +468,8 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.gather = gp;
   static const int poll_env = [] { const char* e = getenv("PBG_POLL_NS"); return e ? atoi(e) : 40; }();
   p.poll_ns = poll_env;
+  static const int defer_env = [] { const char* e = getenv("PBG_GATHER_DEFER"); return e ? atoi(e) : 1; }();
+  p.gather_defer = defer_env;
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
