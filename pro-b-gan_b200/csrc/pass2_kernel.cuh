@@ -4,24 +4,26 @@
 //                 -> D.L0 -> D.L1 (+ final H/2 -> 1 dot, sigmoid) (pro_b_gan_infer.py:207, :302)
 //
 // Activations are handed from layer to layer through L2 (bf16, row-major) with per-row-block arrival counters in
-// global memory: no grid-wide barrier, no launch per layer.  The tiling is cut for the L2 -> SM operand bandwidth
-// that bounds the main loop: two CTAs on one TPC form a pair and compute one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2
+// global memory: no grid-wide barrier, no launch per layer.  The tiling is cut for the L2 -> SM operand bandwidth:
+// two CTAs on one TPC form a pair and compute one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2
 // (M = 256: 128 rows of A per CTA; the BLOCK_N rows of W are split in halves, one per CTA), so a 64-deep k-block
 // costs each SM 16 KB of A + 16 KB of W (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for a single-CTA
-// 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).
+// 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).  This main
+// loop alone sustains 546 clk per k-block on all 148 SMs (floor 512; tools/ubench_pipe.cu).
 //
 //   leader CTA (cluster rank 0)                               peer CTA (rank 1)
 //   warp 0   TMA producer for its halves of A and W           warp 0   TMA producer for its halves of A and W,
 //                                                                      signalling the leader's full barriers
 //   warp 1   MMA issuer (one thread) for the pair             warp 1   scheduler (one thread): pops tickets up to a
-//                                                                      ring's depth ahead, publishes the items to both
-//                                                                      CTAs' rings
+//                                                                      ring's depth ahead, waits for the item's input
+//                                                                      row block, publishes the item to both CTAs
 //   warps 2..9  epilogue of its 128 rows / gather items       warps 2..9  epilogue of its 128 rows / gather items
 //
 // Tickets index a static, topologically ordered item list described by a few segments in the kernel parameters
 // (layer by layer, row-block major).  A pair takes its tickets in order from one atomic counter and works through
 // them in order, which makes any topological order deadlock-free (the unfinished item with the smallest ticket never
-// waits on anything unfinished); the producers poll an item's dependency counter after prefetching its W tiles.
+// waits on anything unfinished).  The scheduler polls an item's dependency counter before publishing it, so the
+// producers never wait between an item's loads: every stage is refilled with W and A the moment it frees.
 // The gather of every row is "phase 0" of the epilogue warps.
 //
 // Epilogues: bias + LeakyReLU -> bf16 -> swizzled staging (double-buffered per warp) -> TMA store; the final
