@@ -39,7 +39,10 @@
 namespace pbg {
 
 constexpr int kP2Stages = 5;
-constexpr int kP2Ring = 4;
+#ifndef PBG_P2RING
+#define PBG_P2RING 4
+#endif
+constexpr int kP2Ring = PBG_P2RING;   // items the scheduler may run ahead of the workers (pre-claimed tickets per pair)
 constexpr int kP2Rows = 256;                        // rows of one pair tile = one dependency block
 constexpr int kP2GroupsPerBlock = kP2Rows / 4;      // 4-row gather groups per block
 constexpr int kP2GatherPerBlock = 4;                // gather items per block: 64 rows = 16 warps x 4 rows
