@@ -177,3 +177,17 @@ def test_bench_product_arm_has_no_cpu_fallback():
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stdout + out.stderr)
+
+
+def test_bench_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1: the driver launches the reference arm like the product arm; rank 0 alone measures and prints."""
+    import json
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611", str(ROOT / "bench.py"), "--impl",
+                          "reference", "--gpus", "2", "--steps", "2", "--warmup", "3", "--batch", "256"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0

@@ -53,3 +53,46 @@ def test_list_inputs_keep_the_reference_error_types():
         hostio.index_rows([[0, 1]], 3)
     assert hostio.index_rows([], 3).shape == (0, 3) and hostio.index_rows((), 1).shape == (0, 1)
     assert hostio.index_rows([(1, 2, 3)], 3).tolist() == [[1, 2, 3]]                      # tuples, as the type hints say
+
+
+def test_parser_fuzz_against_json_loads():
+    """Random well-formed texts (random whitespace, signs, widths) parse to what json.loads + torch.tensor give; random
+    single-character corruptions either still mean the same integers to json.loads or are rejected by both."""
+    import random
+    rnd = random.Random(20261018)
+    ws = ["", " ", "  ", "\n", "\t", "\r\n "]
+    for trial in range(300):
+        cols = rnd.choice([1, 2, 3])
+        rows = rnd.randrange(0, 12)
+        vals = [[rnd.choice([0, 1, -1, rnd.randrange(-10**6, 10**6), rnd.randrange(-2**63, 2**63)]) for _ in range(cols)]
+                for _ in range(rows)]
+        def num(v):
+            return rnd.choice(ws) + str(v) + rnd.choice(ws)
+        if cols == 1:
+            text = rnd.choice(ws) + "[" + ",".join(num(r[0]) for r in vals) + "]" + rnd.choice(ws)
+        else:
+            text = rnd.choice(ws) + "[" + ",".join(rnd.choice(ws) + "[" + ",".join(num(v) for v in r) + "]" + rnd.choice(ws)
+                                                   for r in vals) + "]" + rnd.choice(ws)
+        if rows == 0:
+            text = rnd.choice(ws) + "[" + rnd.choice(ws) + "]"
+        want = torch.tensor(vals, dtype=torch.int64).reshape(rows, cols)
+        assert torch.equal(hostio.parse_index_rows(text, cols), want), text
+        if not text.strip("[] \n\t\r"):
+            continue
+        pos = rnd.randrange(len(text))
+        bad = text[:pos] + rnd.choice("x.,[]- 0e\"") + text[pos + 1:]
+        try:
+            ref = json.loads(bad)
+            ref_t = torch.tensor(ref, dtype=torch.int64)
+            ok_ref = ref_t.numel() == 0 and cols != 1 or (ref_t.dim() == (1 if cols == 1 else 2) and (cols == 1 or ref_t.shape[1] == cols))
+            if any(isinstance(x, float) for x in (ref if cols == 1 else sum((r if isinstance(r, list) else [r] for r in ref), []))):
+                ok_ref = False
+        except Exception:
+            ok_ref = False
+        try:
+            got = hostio.parse_index_rows(bad, cols)
+        except ValueError:
+            got = None
+        if got is not None:       # whatever the C parser accepts, json.loads accepts with the same integers
+            assert ok_ref, (bad, got.tolist())
+            assert got.reshape(-1).tolist() == ref_t.reshape(-1).tolist(), bad
