@@ -129,7 +129,9 @@ int pbg_score_triplets_host(pbg_ctx* ctx, const float* node_emb, int64_t N, cons
                             float* gen_out_host, float* gen_scores_host, float* logits_host,
                             float* probs_host, int64_t B, int precision);
 
-/* Out-of-range ids never fault on the device: the gather clamps them and raises a flag.
+/* Index semantics = the reference's: head / tail ids index `node_emb` as a tensor, so -N..-1 count from the end
+ * (pro_b_gan_infer.py:139, :186, :188); relation ids go through nn.Embedding, which rejects negatives (:187).
+ * Out-of-range ids never fault on the device: the gather clamps them and raises a flag.
  * This synchronises `stream`, returns PBG_ERR_INDEX if the flag was raised since the last
  * check (and clears it), else PBG_OK.  The Python host turns it into IndexError, the
  * exception the reference's `node_emb[heads]` raises (pro_b_gan_infer.py:139). */
