@@ -74,6 +74,7 @@ struct alignas(64) Pass2Params {
   GatherParams gather;
   unsigned layer_mask;
   int gather_defer;      // 1: a gather group's completion wait + arrival ride behind the next group's loads
+  int gather_external;   // 1: xg0 / xd0 were written by a gather kernel before this launch (phase0_groups = 0)
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
   int n_total;          // tickets of this launch
@@ -144,7 +145,7 @@ __device__ __forceinline__ uint32_t bias_leaky_pack(uint32_t a0, uint32_t a1, fl
 }
 
 __device__ __forceinline__ int p2_dep_target(const Pass2Params& p, int dep_kind) {
-  if (dep_kind == DEP_X) return kP2GroupsPerBlock;
+  if (dep_kind == DEP_X) return p.gather_external ? 0 : kP2GroupsPerBlock;
   const int producer = dep_kind == DEP_G0 ? IT_G_L0 : (dep_kind == DEP_D0 ? IT_D_L0 : IT_G_L1);
   return p.layer[producer].n_tiles * kP2WarpsPerPair;
 }

@@ -294,7 +294,7 @@ int pass_grid(const pbg_ctx* c) {
 
 struct Pass;
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores);
+                 void* gen_out, float* scores, bool external_gather);
 
 struct Pass {
   const float* node_emb = nullptr; long long N = 0;
@@ -326,9 +326,17 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   gp.B = rows; gp.err_flag = c->err_flag;
   const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
   if (!bf && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors are a bf16-mode feature");
-  if (!bf) {  // the bf16 mode gathers inside the fused pass kernel
+  // bf16 mode gathers inside the fused pass kernel.  PBG_SPLIT_GATHER=1 (experiment, see DESIGN.md 3.1 "time model"):
+  // the rows are gathered by this small kernel instead -- it fits beside resident pass CTAs of other lanes (no shared
+  // memory, few registers), so a pass no longer holds its SMs through a gather phase with idle tensor pipes.
+  static const bool split_env = [] { const char* e = getenv("PBG_SPLIT_GATHER"); return e && atoi(e) != 0; }();
+  const bool split = bf && split_env && rows > 0;
+  if (!bf) {
     LaunchScope ls(c, PBG_K_GATHER, s);
     gather_concat_kernel<float><<<gather_blocks, 256, 0, s>>>(gp);
+  } else if (split) {
+    LaunchScope ls(c, PBG_K_GATHER, s);
+    gather_concat_kernel<__nv_bfloat16><<<gather_blocks, 256, 0, s>>>(gp);
   }
   PBG_CUDA(c, cudaGetLastError());
 
@@ -337,7 +345,7 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   float* scores = a.gen_scores ? a.gen_scores + off : nullptr;
 
   if (bf) {
-    return launch_pass2(c, w, a, gp, off, rows, gen_out, scores);
+    return launch_pass2(c, w, a, gp, off, rows, gen_out, scores, split);
   } else {
     float *xg0 = (float*)w.xg0, *xd0 = (float*)w.xd0, *bufA = (float*)w.bufA, *bufB = (float*)w.bufB;
     const int row_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
@@ -388,7 +396,7 @@ cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s
 
 // The pair kernel (pass2_kernel.cuh): 256-row blocks, tiles of 256 x {256 | 128}, one CTA pair per tile.
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores) {
+                 void* gen_out, float* scores, bool external_gather) {
   const int grid = pass_grid(c) & ~1;  // whole pairs
   Pass2Params p;
   memset(&p, 0, sizeof p);
@@ -430,7 +438,8 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   // group per warp); the rest of the batch goes through gather items (64 rows each)
   // phase 0 gathers every row (4-row groups, statically spread over the epilogue warps of the grid); every tile is
   // a static ticket, layer by layer (a topological order): the producers poll the dependency counters.
-  p.phase0_groups = nrb * kP2GroupsPerBlock;
+  p.phase0_groups = external_gather ? 0 : nrb * kP2GroupsPerBlock;
+  p.gather_external = external_gather ? 1 : 0;
   {
     // Waves: the row blocks can be cut into `waves` groups whose layer phases are interleaved (L0 of every wave,
     // then L1 of every wave, then L2).  One wave measured best at every size (PBG_WAVES to experiment).
