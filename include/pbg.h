@@ -212,6 +212,16 @@ int pbg_topk(pbg_ctx* ctx, const float* queries, int64_t B, int k, int64_t* out_
  * returns the number of rows in the text (>= 0), or -PBG_ERR_INVALID.  No ctx, no device, thread-safe. */
 int64_t pbg_parse_index_rows(const char* text, size_t len, int cols, int64_t* out, size_t cap_rows);
 
+/* Host-side result formatting; replaces `.tolist()` (pro_b_gan_infer.py:154, :162, :203, :208-209) + the list part of
+ * json.dump(results, indent=2) (:503-508).  Writes the JSON text of a [rows, cols] array (cols == 0: a flat list of
+ * `rows` scalars) exactly as json.dumps prints the corresponding Python list: fp32 values as the repr of the double
+ * they convert to (shortest round-trip digits; NaN / Infinity like json.dumps), one item per line indented by
+ * `indent` spaces per level with the array at nesting depth `depth`; indent < 0 gives the compact ", " form.
+ * Returns the number of bytes the text needs (no terminator); nothing beyond `cap` bytes is written, so call with
+ * out = NULL to size the buffer.  No ctx, no device, thread-safe. */
+int64_t pbg_format_f32_json(const float* v, size_t rows, int cols, int indent, int depth, char* out, size_t cap);
+int64_t pbg_format_i64_json(const int64_t* v, size_t rows, int cols, int indent, int depth, char* out, size_t cap);
+
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t pbg_launch_count(const pbg_ctx* ctx);
 

@@ -30,6 +30,7 @@
 #include "pass2_kernel.cuh"
 #include "topk_kernel.cuh"
 #include "index_rows.cuh"
+#include "json_out.cuh"
 
 using namespace pbg;
 
@@ -558,6 +559,16 @@ int pbg_abi_version(void) { return PBG_ABI_VERSION; }
 const char* pbg_last_error(const pbg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t pbg_launch_count(const pbg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t pbg_format_f32_json(const float* v, size_t rows, int cols, int indent, int depth, char* out, size_t cap) {
+  if ((!v && rows) || cols < 0 || depth < 0) return -(int64_t)fail(nullptr, PBG_ERR_INVALID, "format_f32_json: bad arguments");
+  return (int64_t)pbg_host::format_rows<float>(v, rows, cols, indent, depth, out, cap, pbg_host::put_py_float);
+}
+
+int64_t pbg_format_i64_json(const int64_t* v, size_t rows, int cols, int indent, int depth, char* out, size_t cap) {
+  if ((!v && rows) || cols < 0 || depth < 0) return -(int64_t)fail(nullptr, PBG_ERR_INVALID, "format_i64_json: bad arguments");
+  return (int64_t)pbg_host::format_rows<int64_t>(v, rows, cols, indent, depth, out, cap, pbg_host::put_i64);
+}
 
 int64_t pbg_parse_index_rows(const char* text, size_t len, int cols, int64_t* out, size_t cap_rows) {
   if (!text || cols < 1 || cols > 8) return -(int64_t)fail(nullptr, PBG_ERR_INVALID, "parse_index_rows: null text or cols outside 1..8");

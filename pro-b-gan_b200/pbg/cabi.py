@@ -22,7 +22,7 @@ SYMBOLS = (
     "pbg_load_discriminator", "pbg_generator_forward", "pbg_generator_forward_gather",
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
-    "pbg_set_launch_width", "pbg_set_result_mirrors", "pbg_topk_prepare", "pbg_topk", "pbg_parse_index_rows",
+    "pbg_set_launch_width", "pbg_set_result_mirrors", "pbg_topk_prepare", "pbg_topk", "pbg_parse_index_rows", "pbg_format_f32_json", "pbg_format_i64_json",
 )
 
 
@@ -76,6 +76,8 @@ def load() -> C.CDLL:
         "pbg_topk_prepare": (C.c_int, [vp, vp, i64, vp]),
         "pbg_topk": (C.c_int, [vp, vp, i64, i32, vp, vp, vp]),
         "pbg_parse_index_rows": (i64, [C.c_char_p, sz, i32, vp, sz]),
+        "pbg_format_f32_json": (i64, [vp, sz, i32, i32, i32, vp, sz]),
+        "pbg_format_i64_json": (i64, [vp, sz, i32, i32, i32, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

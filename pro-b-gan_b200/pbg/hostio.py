@@ -8,6 +8,7 @@ through numpy's C converter.  Like the reference, non-integer ids are an IndexEr
 from __future__ import annotations
 
 import ctypes as C
+import json
 
 import numpy as np
 import torch
@@ -56,3 +57,62 @@ def index_rows(x, cols: int, pin: bool = False) -> torch.Tensor:
         raise ValueError(f"expected [rows, {cols}] ids, got shape {tuple(t.shape)}")
     t = t.contiguous()
     return t.pin_memory() if pin and t.numel() else t
+
+
+# ---------------------------------------------------------------------------------------------- results -> JSON text
+def _array_json(a, indent: int, depth: int) -> str:
+    """JSON text of a 1-D / 2-D float32 or integer array, byte for byte what json.dumps prints for ``a.tolist()``."""
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    if a.ndim not in (1, 2):
+        raise ValueError(f"result arrays are 1-D or 2-D, got shape {a.shape}")
+    lib = cabi.load()
+    if a.dtype.kind == "f":
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        fn = lib.pbg_format_f32_json
+    elif a.dtype.kind in "iu":
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        fn = lib.pbg_format_i64_json
+    else:
+        raise ValueError(f"cannot format dtype {a.dtype}")
+    rows, cols = (a.shape[0], 0) if a.ndim == 1 else a.shape
+    if a.ndim == 2 and cols == 0:                       # [[], [], ...]: no C fast path needed
+        return _indent_tail(json.dumps(a.tolist(), indent=indent if indent >= 0 else None), indent, depth)
+    per = 28 + max(indent, 0) * (depth + 3) + 2
+    cap = a.size * per + rows * per + 64
+    buf = C.create_string_buffer(cap)
+    need = fn(C.c_void_p(a.ctypes.data), rows, cols, indent, depth, buf, cap)
+    if need < 0:
+        raise ValueError(cabi.last_error(None))
+    if need > cap:                                      # the estimate is generous; never truncate silently
+        buf = C.create_string_buffer(need)
+        need = fn(C.c_void_p(a.ctypes.data), rows, cols, indent, depth, buf, need)
+    return buf.raw[:need].decode("ascii")
+
+
+def _indent_tail(text: str, indent: int, depth: int) -> str:
+    if indent < 0 or depth == 0:
+        return text
+    pad = " " * (indent * depth)
+    return text.replace("\n", "\n" + pad)
+
+
+def dumps_results(results: dict, indent: int = 2) -> str:
+    """``json.dumps(results, indent=indent)`` (pro_b_gan_infer.py:505-508) for a result dictionary whose top-level
+    values may be arrays / tensors (``FusedInference(..., as_arrays=True)``): those are written by the C formatter
+    without ever becoming Python lists; everything else goes through json.dumps.  The text is identical to what
+    json.dumps prints for the same dictionary with ``.tolist()`` applied to the arrays."""
+    import json as _json
+    if not results:
+        return "{}"
+    pad = " " * max(indent, 0)
+    items = []
+    for k, v in results.items():
+        if isinstance(v, (np.ndarray, torch.Tensor)):
+            body = _array_json(v, indent, 1)
+        else:
+            body = _indent_tail(_json.dumps(v, indent=indent if indent >= 0 else None), indent, 1)
+        items.append(_json.dumps(k) + ": " + body)
+    if indent < 0:
+        return "{" + ", ".join(items) + "}"
+    return "{\n" + ",\n".join(pad + it for it in items) + "\n}"

@@ -107,11 +107,14 @@ class FusedInference:
         return rows[:, 0].tolist() if flat else rows.tolist()
 
     # ------------------------------------------------------------------ :167-211
-    def score_triplets(self, triplets, method: str = "both") -> Dict[str, Any]:
+    def score_triplets(self, triplets, method: str = "both", as_arrays: bool = False) -> Dict[str, Any]:
+        """``as_arrays=True`` returns numpy arrays instead of Python lists (same keys, same values): no ``.tolist()``,
+        and ``pbg.hostio.dumps_results`` writes them as the JSON text json.dumps would print for the lists."""
         trip = self._stage_rows("trip", triplets, 3)
         B = trip.shape[0]
+        out = (lambda t: t.numpy().copy()) if as_arrays else (lambda t: t.tolist())   # staging buffers are reused
         results: Dict[str, Any] = {
-            "triplets": self._echo(triplets, trip),
+            "triplets": trip.numpy().copy() if as_arrays else self._echo(triplets, trip),
             "metadata": {"num_triplets": B, "method": method, "model_hit10": self.best_val_hit10},
         }
         if B == 0:
@@ -127,15 +130,17 @@ class FusedInference:
             self.engine.score_triplets_host(self.node_emb, self.rel_weight, trip, z, None, scores, logits, probs,
                                             precision=self.precision)   # raises IndexError on a bad id
         if run_g:
-            results["generator_scores"] = scores.tolist()
+            results["generator_scores"] = out(scores)
         if run_d:
-            results["discriminator_logits"] = logits.tolist()
-            results["discriminator_probabilities"] = probs.tolist()
+            results["discriminator_logits"] = out(logits)
+            results["discriminator_probabilities"] = out(probs)
         return results
 
     # ------------------------------------------------------------------ :118-165
-    def predict_tails(self, head_relation_pairs, top_k: int = 10, return_scores: bool = False) -> Dict[str, Any]:
+    def predict_tails(self, head_relation_pairs, top_k: int = 10, return_scores: bool = False,
+                      as_arrays: bool = False) -> Dict[str, Any]:
         pairs = self._stage_rows("pairs", head_relation_pairs, 2)
+        out = (lambda t: t.cpu().numpy()) if as_arrays else (lambda t: t.tolist())
         B = pairs.shape[0]
         with torch.no_grad(), torch.cuda.device(self.device):
             dev_pairs = pairs.to(self.device, non_blocking=True)
@@ -145,11 +150,11 @@ class FusedInference:
             top_scores, top_idx = self.engine.cosine_topk(pred, self.node_emb, top_k)
             self.engine.check_indices()
             results: Dict[str, Any] = {
-                "predictions": top_idx.tolist(),
+                "predictions": out(top_idx),
                 "metadata": {"num_queries": B, "top_k": top_k, "model_hit10": self.best_val_hit10},
             }
             if return_scores:
-                results["scores"] = top_scores.tolist()
+                results["scores"] = out(top_scores)
         return results
 
     # ------------------------------------------------------------------ :213-263

@@ -193,3 +193,26 @@ def test_missing_checkpoint_and_cpu_device_fail_loudly(tmp_path, ckpt_path):
         FusedInference(str(tmp_path / "nope.pt"), "cuda")
     with pytest.raises(RuntimeError):
         FusedInference(ckpt_path, "cpu")
+
+
+def test_as_arrays_and_the_c_writer_reproduce_the_json_document(inf):
+    """score_triplets / predict_tails with as_arrays=True + pbg.hostio.dumps_results give the very text
+    json.dumps(results, indent=2) prints for the list form (the reference's output step, :505-508)."""
+    import numpy as np
+    from pbg import hostio
+    trip = gold_json("config1_score_triplets.json")["triplets"]
+    inf.generator.reseed()
+    lists = inf.score_triplets(trip)
+    inf.generator.reseed()
+    arrays = inf.score_triplets(trip, as_arrays=True)
+    assert list(arrays) == list(lists) and isinstance(arrays["generator_scores"], np.ndarray)
+    assert hostio.dumps_results(arrays, indent=2) == json.dumps(lists, indent=2)
+    inf.generator.reseed()
+    again = inf.score_triplets(trip[:5], as_arrays=True)            # the arrays own their memory: a later call does not
+    assert arrays["discriminator_logits"].tolist() == lists["discriminator_logits"] and len(again["triplets"]) == 5
+    pairs = [[t[0], t[1]] for t in trip]
+    inf.generator.reseed()
+    pl = inf.predict_tails(pairs, top_k=10, return_scores=True)
+    inf.generator.reseed()
+    pa = inf.predict_tails(pairs, top_k=10, return_scores=True, as_arrays=True)
+    assert hostio.dumps_results(pa, indent=2) == json.dumps(pl, indent=2)

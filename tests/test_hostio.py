@@ -96,3 +96,53 @@ def test_parser_fuzz_against_json_loads():
         if got is not None:       # whatever the C parser accepts, json.loads accepts with the same integers
             assert ok_ref, (bad, got.tolist())
             assert got.reshape(-1).tolist() == ref_t.reshape(-1).tolist(), bad
+
+
+def _special_floats():
+    import struct
+    vals = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1e-4, 9.9999e-5, 1e-5, 1.5e-7, 1e15, 1e16, 9.999999e15, 1.2345678e17, 3.4028235e38,
+            1.17549435e-38, 1e-45, 123456.789, 100.0, 1e7, 16777216.0, 0.30000001192092896, float("inf"), float("-inf"), float("nan")]
+    vals += [struct.unpack("<f", struct.pack("<I", b))[0] for b in (0x00000001, 0x007FFFFF, 0x00800000, 0x3F800001, 0x7F7FFFFF, 0x4B000000, 0x38D1B717)]
+    return np.asarray(vals, dtype=np.float32)
+
+
+def test_result_writer_reproduces_json_dumps_byte_for_byte():
+    """pbg_format_f32_json / pbg_format_i64_json + dumps_results == json.dumps(results with .tolist(), indent=2), the
+    reference's output step (pro_b_gan_infer.py:505-508): Python float repr of every fp32 value, same layout."""
+    rng = np.random.default_rng(7)
+    f = np.concatenate([_special_floats(), rng.standard_normal(3000).astype(np.float32),
+                        (rng.standard_normal(2000) * 10.0 ** rng.integers(-30, 30, 2000)).astype(np.float32),
+                        rng.integers(0, 2**32, 3000, dtype=np.uint64).astype(np.uint32).view(np.float32)])   # any bit pattern
+    ints = np.concatenate([rng.integers(-2**63, 2**63 - 1, 500), np.asarray([0, -1, 1, 2**63 - 1, -2**63, 65535])])
+    res = {
+        "triplets": rng.integers(0, 65536, (257, 3)),
+        "metadata": {"num_triplets": 257, "method": "both", "model_hit10": 0.4242, "nested": {"a": [1, 2.5, None]}},
+        "generator_scores": f,
+        "predictions": ints[:500].reshape(50, 10),
+        "scores": torch.from_numpy(f[:4000].reshape(400, 10).copy()),
+        "empty": np.zeros(0, dtype=np.float32),
+        "empty_rows": np.zeros((0, 3), dtype=np.int64),
+        "a_list": [1, 2, 3],
+        "a_string": "x\"y\u00e9",
+    }
+    ref = {k: (v.tolist() if isinstance(v, (np.ndarray, torch.Tensor)) else v) for k, v in res.items()}
+    for indent in (2, 1, 4, 0):
+        assert hostio.dumps_results(res, indent=indent) == json.dumps(ref, indent=indent)
+    assert hostio.dumps_results(res, indent=-1) == json.dumps(ref)
+    assert hostio.dumps_results({}) == json.dumps({}, indent=2)
+    back = json.loads(hostio.dumps_results({"x": f[np.isfinite(f)]}))["x"]
+    assert np.array_equal(np.asarray(back, dtype=np.float32), f[np.isfinite(f)])          # and it round-trips exactly
+
+
+def test_result_writer_sizes_its_buffer():
+    import ctypes as C
+    from pbg import cabi
+    lib = cabi.load()
+    a = np.asarray([1.5, -2.25e-7, 3.0], dtype=np.float32)
+    need = lib.pbg_format_f32_json(C.c_void_p(a.ctypes.data), 3, 0, 2, 0, None, 0)
+    want = json.dumps(a.tolist(), indent=2)
+    assert need == len(want)
+    small = C.create_string_buffer(4)
+    assert lib.pbg_format_f32_json(C.c_void_p(a.ctypes.data), 3, 0, 2, 0, small, 4) == need   # never writes past cap
+    buf = C.create_string_buffer(need)
+    assert lib.pbg_format_f32_json(C.c_void_p(a.ctypes.data), 3, 0, 2, 0, buf, need) == need and buf.raw[:need].decode() == want
