@@ -68,5 +68,10 @@ for B in (16, 4096, 32768):
     b = timeit(lambda: inf.score_triplets(text), n)
     trip = synth.make_triplets(B)
     c = timeit(lambda: inf.score_triplets(trip), n)
+    from pbg import hostio
+    d = timeit(lambda: json.dumps(script_style(text), indent=2), max(2, n // 4))          # JSON text in -> JSON text out
+    e = timeit(lambda: hostio.dumps_results(inf.score_triplets(text, as_arrays=True), indent=2), max(2, n // 4))
+    P(f"score_triplets CLI round trip (JSON text in -> JSON text out, indent=2), B={B:6d}: script-style {d:8.2f} ms | "
+      f"fused host + C reader / writer {e:7.2f} ms ({d / e:.1f}x)")
     P(f"score_triplets request, B={B:6d}: script-style over the CUDA modules {a:8.2f} ms | fused host from JSON text {b:7.2f} ms "
       f"({a / b:.1f}x) | fused host from an int64 tensor {c:7.2f} ms ({B / c / 1e3:.2f} M triplets/s; latent draw on the CPU included)")
