@@ -129,6 +129,27 @@ int pbg_score_triplets_host(pbg_ctx* ctx, const float* node_emb, int64_t N, cons
                             float* gen_out_host, float* gen_scores_host, float* logits_host,
                             float* probs_host, int64_t B, int precision);
 
+/* Request staging -- the ingest / compute split of the same pass for callers that keep requests in flight.
+ * pbg_score_triplets does gather -> layers in one launch, so the first tiles of every pass wait for its gather.
+ * A server (or bench.py) that already holds the NEXT request's ids and latents on the device can stage it while the
+ * current pass runs:
+ *   pbg_stage_triplets(ctx, slot, ...)  gathers + concatenates + casts the request's rows (`h = node_emb[heads]`,
+ *       `rel_emb(relations)`, `node_emb[tails]`, pro_b_gan_infer.py:186-188, and the latent concat inside G) into
+ *       staging slot `slot` (0 or 1) of the ctx, as a small kernel on `stream` (an ingest stream) that fits beside
+ *       resident pass CTAs; want_gen / want_disc choose the operands built; B <= 65536.
+ *   pbg_score_staged(ctx, slot, ...)    runs the G + D pass over the staged rows on `stream` (the compute stream);
+ *       results as in pbg_score_triplets.  bf16 mode only.
+ * Both are stream-ordered; the CALLER orders a slot's uses across the two streams (stage -> score -> next stage of the
+ * same slot: two events, or one stream).  A ctx still runs one pass at a time.
+ * pbg_reserve sizes the activation workspace (and `stage_slots` staging slots) for `rows` rows up front: buffers
+ * otherwise grow lazily with a device synchronisation, which is refused (PBG_ERR_INVALID) while the stream is being
+ * captured into a CUDA graph. */
+int pbg_reserve(pbg_ctx* ctx, int64_t rows, int precision, int stage_slots);
+int pbg_stage_triplets(pbg_ctx* ctx, int slot, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                       const int64_t* triplets, const float* z, int64_t B, int want_gen, int want_disc, void* stream);
+int pbg_score_staged(pbg_ctx* ctx, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits,
+                     float* probs, void* stream);
+
 /* Index semantics = the reference's: head / tail ids index `node_emb` as a tensor, so -N..-1 count from the end
  * (pro_b_gan_infer.py:139, :186, :188); relation ids go through nn.Embedding, which rejects negatives (:187).
  * Out-of-range ids never fault on the device: the gather clamps them and raises a flag.

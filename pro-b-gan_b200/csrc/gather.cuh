@@ -83,15 +83,15 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const GatherParams p
     } else {
       rrow = p.r + b * p.E;
     }
-    if (xd != nullptr) {
-      if (p.tails != nullptr) {
-        long long i = p.tails[b * p.tail_stride];
-        if (i < 0) i += p.N;
-        if (i < 0 || i >= p.N) { bad = true; i = 0; }
-        trow = p.node_emb + i * p.E;
-      } else {
-        trow = p.t + b * p.E;
-      }
+    // tail ids are range-checked whenever they are given -- a generator-only pass reads them too (cosine against
+    // node_emb[tail], pro_b_gan_infer.py:188, :202), and the reference raises IndexError for every method
+    if (p.tails != nullptr) {
+      long long i = p.tails[b * p.tail_stride];
+      if (i < 0) i += p.N;
+      if (i < 0 || i >= p.N) { bad = true; i = 0; }
+      trow = p.node_emb + i * p.E;
+    } else if (xd != nullptr) {
+      trow = p.t + b * p.E;
     }
     if (bad && lane == 0) atomicOr(p.err_flag, 1);
 
@@ -117,6 +117,64 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(const GatherParams p
       for (int v = (3 * p.E) / 4 + lane; v < p.ldd / 4; v += 32)
         store4<T>(d + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+  }
+}
+
+// Request staging (pbg_stage_triplets): the same gather + concat + bf16 cast as above for one request, plus an fp32 copy
+// of the tail rows in request order (the cosine epilogue of the pass then reads rows, not indices).  Runs on the
+// caller's ingest stream BESIDE the pass kernels of earlier requests: small blocks (128 threads, <= 40 registers, no
+// shared memory) fit into what a resident pass CTA leaves free on an SM (~11k registers, 1700 threads).  One warp per
+// row, every load of the row in flight before the first store.  HBM/L2-bound: (3E + Z) * 4 bytes read and
+// (2E + Z + 3E) * 2 + 4E bytes written per row.
+struct StageParams {
+  GatherParams g;
+  float* xt;   // [B, E] fp32 tail rows, or null
+};
+__global__ void __launch_bounds__(128, 12) stage_rows_kernel(const __grid_constant__ StageParams sp) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long num_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int E = sp.g.E, Z = sp.g.Z, E4 = E >> 2, Z4 = Z >> 2;
+  const long long N = sp.g.N;
+  __nv_bfloat16* const xg = static_cast<__nv_bfloat16*>(sp.g.xg);
+  __nv_bfloat16* const xd = static_cast<__nv_bfloat16*>(sp.g.xd);
+  for (long long b = warp_global; b < sp.g.B; b += num_warps) {
+    bool bad = false;
+    long long hi = sp.g.heads[b * 3], ri = sp.g.rels[b * 3], ti = sp.g.tails[b * 3];   // [B, 3] int64 rows
+    if (hi < 0) hi += N;   // node_emb[idx] is tensor indexing: -N..-1 count from the end (pro_b_gan_infer.py:186, :188)
+    if (ti < 0) ti += N;
+    if (hi < 0 || hi >= N) { bad = true; hi = 0; }
+    if (ri < 0 || ri >= sp.g.R) { bad = true; ri = 0; }   // nn.Embedding rejects negative ids (:187)
+    if (ti < 0 || ti >= N) { bad = true; ti = 0; }
+    if (bad && lane == 0) atomicOr(sp.g.err_flag, 1);
+    const float* hrow = sp.g.node_emb + hi * E;
+    const float* rrow = sp.g.rel_emb + ri * E;
+    const float* trow = sp.g.node_emb + ti * E;
+    __nv_bfloat16* g = xg ? xg + b * sp.g.ldg : nullptr;
+    __nv_bfloat16* d = xd ? xd + b * sp.g.ldd : nullptr;
+    for (int v = lane; v < E4; v += 32) {
+      const float4 hv = ld_stream4(hrow + 4 * v);
+      const float4 rv = ld_stream4(rrow + 4 * v);
+      const float4 tv = ld_stream4(trow + 4 * v);
+      if (g) {
+        store4<__nv_bfloat16>(g + 4 * v, hv);
+        store4<__nv_bfloat16>(g + E + 4 * v, rv);
+      }
+      if (d) {
+        store4<__nv_bfloat16>(d + 4 * v, hv);
+        store4<__nv_bfloat16>(d + E + 4 * v, rv);
+        store4<__nv_bfloat16>(d + 2 * E + 4 * v, tv);
+      }
+      if (sp.xt) store4<float>(sp.xt + b * E + 4 * v, tv);
+    }
+    if (g) {
+      for (int v = lane; v < Z4; v += 32) store4<__nv_bfloat16>(g + 2 * E + 4 * v, ld_stream4(sp.g.z + b * Z + 4 * v));
+      for (int v = (2 * E + Z) / 4 + lane; v < sp.g.ldg / 4; v += 32)
+        store4<__nv_bfloat16>(g + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    if (d)
+      for (int v = (3 * E) / 4 + lane; v < sp.g.ldd / 4; v += 32)
+        store4<__nv_bfloat16>(d + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
   }
 }
 

@@ -102,6 +102,7 @@ struct alignas(64) Pass2Params {
   int n_mirror;
   void* mir_gen[kMaxMirrors]; float* mir_cos[kMaxMirrors]; float* mir_logits[kMaxMirrors]; float* mir_probs[kMaxMirrors];
   long long* trace;
+  int dbg;   // diagnostics instance only (PBG_DBG): bit mask of epilogue parts to leave out, see tools/trace_pass.py
 };
 static_assert(sizeof(Pass2Params) <= 4096, "kernel parameter space");
 
@@ -182,7 +183,9 @@ __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, 
   uint32_t spins = 0;
   while (ld_relaxed_gpu(ctr) < target) {
     __nanosleep(p.poll_ns);
+#if PBG_HANG_GUARD
     if (++spins > 4000000u) pbg_wait_timed_out("dependency (kind, row block)", dep_kind, rb);
+#endif
   }
   fence_proxy_async_all();
 }
@@ -245,9 +248,10 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
       } else if (which == 1) {
         if (g.rels) { long long i = g.rels[row * g.rel_stride]; if (i < 0 || i >= g.R) { bad = true; i = 0; } src = g.rel_emb + i * g.E; }
         else src = g.r + row * g.E;
+      } else if (g.tails) {   // range-checked whenever tail ids are given: a generator-only pass reads them too (cosine)
+        long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E;
       } else if (xd != nullptr) {
-        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
-        else src = g.t + row * g.E;
+        src = g.t + row * g.E;
       }
     }
   }
@@ -450,7 +454,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const int kind = it.x & 0xff;
         if (kind == IT_END) break;
         long long* ti = (tr && n_items < kTraceItems) ? tr + 16 + 4 * n_items : nullptr;
-        if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; ti[1] = 0; }
+        if (ti) { ti[0] = (clock64() << 20) | (static_cast<long long>(it.y & 0xfff) << 8) | kind; }
         ++n_items;
         const int n_blk = (it.x >> 8) & 0xff;
         const int rb = static_cast<int>(it.y);
@@ -459,7 +463,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const uint32_t bytes_pair = 2u * (L::kA + static_cast<uint32_t>(w_rows) * kBlockK * 2);
         const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
         const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
-        if (ti) ti[1] = clock64();
         for (int kb = 0; kb < ly.num_kb; ++kb) {
           if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
           else mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -479,6 +482,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
       long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0, lat_sum = 0, lat_n = 0, lat_max = 0;
+      int n_it = 0;
       for (;;) {
         if (tr) { const long long t = clock64(); mbar_wait(&sched_full[slot], sphase); w_item += clock64() - t; }
         else mbar_wait(&sched_full[slot], sphase);
@@ -492,6 +496,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (tr) { const long long t = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
         else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (tr && n_it < kTraceItems) tr[16 + 4 * n_it + 1] = clock64();   // this item's accumulator stage is free: MMA start
+        ++n_it;
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < ly.num_kb; ++kb) {
           if (tr) {
@@ -596,10 +602,14 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (want_cos) {
         const float* trow = nullptr;
         if (row_ok) {
-          long long tid = p.tail_idx[grow * p.tail_stride];
-          if (tid < 0) tid += p.n_ent;                  // same wrap as the gather
-          tid = (tid < 0 || tid >= p.n_ent) ? 0 : tid;  // the gather has already flagged it
-          trow = p.tail_tab + tid * p.n_valid;
+          if (p.tail_idx != nullptr) {
+            long long tid = p.tail_idx[grow * p.tail_stride];
+            if (tid < 0) tid += p.n_ent;                  // same wrap as the gather
+            tid = (tid < 0 || tid >= p.n_ent) ? 0 : tid;  // the gather has flagged it (tails are checked whenever given)
+            trow = p.tail_tab + tid * p.n_valid;
+          } else {
+            trow = p.tail_tab + grow * p.n_valid;         // staged request: tail rows in request order
+          }
         }
         trow_bits = reinterpret_cast<unsigned long long>(trow);
         if (half < n_chunks) {
@@ -627,14 +637,15 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const int row0 = rb * kP2Rows + static_cast<int>(rank) * 128 + q * 32;
         // 32-column TMEM loads, software pipelined: the next load is in flight while the previous one is converted
         uint32_t va[32], vb[32];
-        if (half < n_chunks) tmem_ld_32x32_ptr(taddr + half * 64, va);
+        const int dbg = TR ? p.dbg : 0;
+        if (half < n_chunks && !(dbg & 8)) tmem_ld_32x32_ptr(taddr + half * 64, va);
         for (int c = half; c < n_chunks; c += 2) {
           if (tp) tq0 = clock64();
           const float4* b4 = reinterpret_cast<const float4*>(bias_tile + c * 64);
           if (tp) tq1 = clock64();
           uint8_t* sbuf = st;
           tmem_ld_wait();
-          tmem_ld_32x32_ptr(taddr + c * 64 + 32, vb);
+          if (!(dbg & 8)) tmem_ld_32x32_ptr(taddr + c * 64 + 32, vb);
           if (tp) tq2 = clock64();
           {
             float4 bq[8];
@@ -653,7 +664,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 4; ++t) *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w[t];
+            for (int t = 0; t < 4; ++t) if (!(dbg & 4)) *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((t ^ (lane & 7)) << 4)) = w[t];
           }
           float4 bq[8];
 #pragma unroll
@@ -662,7 +673,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           tmem_ld_wait();
           if (tp) tq6 = clock64();
           if (c + 2 < n_chunks) {
-            tmem_ld_32x32_ptr(taddr + (c + 2) * 64, va);
+            if (!(dbg & 8)) tmem_ld_32x32_ptr(taddr + (c + 2) * 64, va);
           } else {  // this warp's last read of the accumulator stage
             tc_fence_before();
             __syncwarp();
@@ -676,13 +687,13 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
             w.y = bias_leaky_pack(vb[8 * t + 2], vb[8 * t + 3], ba.z, ba.w, slope);
             w.z = bias_leaky_pack(vb[8 * t + 4], vb[8 * t + 5], bb.x, bb.y, slope);
             w.w = bias_leaky_pack(vb[8 * t + 6], vb[8 * t + 7], bb.z, bb.w, slope);
-            *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((4 + t) ^ (lane & 7)) << 4)) = w;
+            if (!(dbg & 4)) *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((4 + t) ^ (lane & 7)) << 4)) = w;
           }
           if (tp) tq3 = clock64();
-          fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
+          if (!(dbg & 2)) fence_proxy_async_smem();  // generic-proxy writes of the staging tile -> visible to the bulk store
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
+            if (!(dbg & 1)) tma_store_2d(&p.tm_o[kind], sbuf, n0 + c * 64, row0);
             tma_store_commit();
           }
           if (tp) { tq4 = clock64(); ph_wr += tq1 - tq0; ph_ld += tq2 - tq1; ph_math += tq3 - tq2; ph_st += tq4 - tq3; ph_n += 1; ph_m1 += tq5 - tq2; ph_w2 += tq6 - tq5; }

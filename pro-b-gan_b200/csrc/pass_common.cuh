@@ -97,9 +97,10 @@ __device__ __forceinline__ void pass_gather_group(const GatherParams& g, long lo
       } else if (which == 1) {
         if (g.rels) { long long i = g.rels[row * g.rel_stride]; if (i < 0 || i >= g.R) { bad = true; i = 0; } src = g.rel_emb + i * g.E; }
         else src = g.r + row * g.E;
+      } else if (g.tails) {   // range-checked whenever tail ids are given: a generator-only pass reads them too (cosine)
+        long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E;
       } else if (xd != nullptr) {
-        if (g.tails) { long long i = g.tails[row * g.tail_stride]; if (i < 0) i += g.N; if (i < 0 || i >= g.N) { bad = true; i = 0; } src = g.node_emb + i * g.E; }
-        else src = g.t + row * g.E;
+        src = g.t + row * g.E;
       }
     }
   }

@@ -77,6 +77,17 @@ struct TopkState {
   size_t cand_cap = 0; float* cand_score = nullptr; int* cand_idx = nullptr; float* cand_tau = nullptr; int* flag = nullptr;
 };
 
+// One staged request (pbg_stage_triplets): the first-layer operands of the pass, gathered + concatenated + cast by the
+// staging kernel on the caller's ingest stream while the previous request's pass is still running.
+struct StageSlot {
+  long long cap = 0;  // rows allocated
+  void *xg0 = nullptr, *xd0 = nullptr;
+  float* xt = nullptr;  // fp32 tail rows [cap, E] for the cosine epilogue
+  CUtensorMap tm_xg0, tm_xd0;
+  long long B = -1;     // rows of the staged request (-1: nothing staged)
+  bool has_g = false, has_d = false;
+};
+
 thread_local std::string g_create_error;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -95,6 +106,7 @@ struct pbg_ctx {
   float* d_w3_pad = nullptr;  // [hd2p]
   float d_b3 = 0.f;
   Workspace ws_bf16, ws_f32;
+  StageSlot stage[2];
   int* err_flag = nullptr;       // device
   int* err_flag_host = nullptr;  // pinned
   cudaStream_t own_stream = nullptr;
@@ -201,9 +213,25 @@ int upload_linear(pbg_ctx* c, Linear& l, int n, int k, int kp, const float* w_ho
   return make_tmap(c, &l.tmap_w, l.w_bf16, l.np, l.kp, l.block_n);
 }
 
-int ensure_ws(pbg_ctx* c, int prec, long long rows) {
+// Growing a buffer means cudaDeviceSynchronize + cudaFree + cudaMalloc: illegal while `s` is being captured into a
+// CUDA graph, and a device-wide stall for every other lane otherwise -- callers that care size everything up front
+// with pbg_reserve().
+int refuse_growth_in_capture(pbg_ctx* c, cudaStream_t s, const char* what) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+    return fail(c, PBG_ERR_INVALID, "%s must grow while the stream is being captured: call pbg_reserve() first", what);
+  return PBG_OK;
+}
+
+void free_stage(StageSlot& st) {
+  cudaFree(st.xg0); cudaFree(st.xd0); cudaFree(st.xt);
+  st = StageSlot{};
+}
+
+int ensure_ws(pbg_ctx* c, int prec, long long rows, cudaStream_t stream) {
   Workspace& w = prec == PBG_PREC_BF16 ? c->ws_bf16 : c->ws_f32;
   if (w.rows >= rows) return PBG_OK;
+  PBG_TRY(refuse_growth_in_capture(c, stream, "the workspace"));
   // round the capacity up so that small calls do not keep reallocating
   long long cap = 1024;
   while (cap < rows) cap *= 2;
@@ -244,6 +272,24 @@ int ensure_ws(pbg_ctx* c, int prec, long long rows) {
     PBG_CUDA(c, cudaMalloc(&w.bufB, es * cap * hm));
   }
   w.rows = cap;
+  return PBG_OK;
+}
+
+int ensure_stage(pbg_ctx* c, StageSlot& st, long long rows, cudaStream_t stream) {
+  if (st.cap >= rows) return PBG_OK;
+  PBG_TRY(refuse_growth_in_capture(c, stream, "a staging slot"));
+  long long cap = 1024;
+  while (cap < rows) cap *= 2;
+  cap = std::min(cap, kMaxChunk);
+  PBG_CUDA(c, cudaDeviceSynchronize());  // nothing may still be reading the old buffers
+  free_stage(st);
+  const size_t es = sizeof(__nv_bfloat16);
+  PBG_CUDA(c, cudaMalloc(&st.xg0, es * cap * c->kg0p));
+  PBG_CUDA(c, cudaMalloc(&st.xd0, es * cap * c->kd0p));
+  PBG_CUDA(c, cudaMalloc(&st.xt, sizeof(float) * cap * c->dims.embed_dim));
+  PBG_TRY(make_tmap(c, &st.tm_xg0, st.xg0, cap, c->kg0p, kBlockM));
+  PBG_TRY(make_tmap(c, &st.tm_xd0, st.xd0, cap, c->kd0p, kBlockM));
+  st.cap = cap;
   return PBG_OK;
 }
 
@@ -295,7 +341,7 @@ int pass_grid(const pbg_ctx* c) {
 
 struct Pass;
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores, bool external_gather);
+                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot = nullptr);
 
 struct Pass {
   const float* node_emb = nullptr; long long N = 0;
@@ -397,12 +443,14 @@ cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s
 
 // The pair kernel (pass2_kernel.cuh): 256-row blocks, tiles of 256 x {256 | 128}, one CTA pair per tile.
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores, bool external_gather) {
+                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot) {
   const int grid = pass_grid(c) & ~1;  // whole pairs
   Pass2Params p;
   memset(&p, 0, sizeof p);
   const Linear* lin[5] = {&c->g[0], &c->d[0], &c->g[1], &c->d[1], &c->g[2]};
-  const CUtensorMap* amap[5] = {&w.tm_xg0, &w.tm_xd0, &w.tm_bufA_g, &w.tm_bufD_d, &w.tm_bufB_g};
+  // first-layer operands: the ctx's own gather buffers, or a staged request's (pbg_stage_triplets)
+  const CUtensorMap* amap[5] = {slot ? &slot->tm_xg0 : &w.tm_xg0, slot ? &slot->tm_xd0 : &w.tm_xd0, &w.tm_bufA_g, &w.tm_bufD_d,
+                                &w.tm_bufB_g};
   const CUtensorMap* omap[5] = {&w.tmo_bufA, &w.tmo_bufD, &w.tmo_bufB, nullptr, nullptr};
   const bool on[5] = {a.run_g, a.run_d, a.run_g, a.run_d, a.run_g};
   static const int pred_of[5] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1};
@@ -483,7 +531,9 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
-  if (scores) {
+  if (scores && slot) {   // the staging kernel left the tail rows, in request order, in the slot: no index, no table
+    p.cosine = scores; p.tail_tab = slot->xt; p.n_ent = slot->cap; p.tail_idx = nullptr; p.tail_stride = 0;
+  } else if (scores) {
     p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
     p.tail_idx = a.tails + off * a.ts; p.tail_stride = a.ts;
   }
@@ -493,6 +543,7 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.probs = a.probs ? a.probs + off : nullptr;
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
+  { static const int dbg_env = [] { const char* e = getenv("PBG_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg_env; }
   p.n_mirror = c->n_mirror;
   for (int i = 0; i < c->n_mirror; ++i) {
     if (gen_out && !c->mir_gen[i]) return fail(c, PBG_ERR_INVALID, "result mirror %d has no gen_out buffer", i);
@@ -545,7 +596,7 @@ int run_pass(pbg_ctx* c, const Pass& a) {
   if (a.B == 0 || (!a.run_g && !a.run_d)) return PBG_OK;
   PBG_CUDA(c, cudaSetDevice(c->dims.device));
   const long long chunk = std::min(a.B, kMaxChunk);
-  PBG_TRY(ensure_ws(c, a.prec, chunk));
+  PBG_TRY(ensure_ws(c, a.prec, chunk, a.stream));
   for (long long off = 0; off < a.B; off += chunk) PBG_TRY(run_chunk(c, a, off, std::min(chunk, a.B - off)));
   return PBG_OK;
 }
@@ -771,6 +822,7 @@ void pbg_destroy(pbg_ctx* c) {
   for (auto& l : c->d) free_linear(l);
   cudaFree(c->d_w3); cudaFree(c->d_w3_pad);
   free_ws(c->ws_bf16); free_ws(c->ws_f32);
+  free_stage(c->stage[0]); free_stage(c->stage[1]);
   cudaFree(c->err_flag); cudaFree(c->trace);
   cudaFree(c->tk.tn); cudaFree(c->tk.inv_t); cudaFree(c->tk.qn); cudaFree(c->tk.inv_q);
   cudaFree(c->tk.cand_score); cudaFree(c->tk.cand_idx); cudaFree(c->tk.cand_tau); cudaFree(c->tk.flag);
@@ -875,6 +927,69 @@ int pbg_score_triplets(pbg_ctx* c, const float* node_emb, int64_t N, const float
   a.run_g = (gen_out != nullptr || gen_scores != nullptr); a.run_d = (logits != nullptr);
   a.B = B; a.prec = precision; a.stream = (cudaStream_t)stream;
   return run_pass(c, a);
+}
+
+int pbg_reserve(pbg_ctx* c, int64_t rows, int precision, int stage_slots) {
+  if (!c) return PBG_ERR_INVALID;
+  if (rows <= 0) return fail(c, PBG_ERR_INVALID, "reserve: rows must be positive");
+  if (precision != PBG_PREC_F32 && precision != PBG_PREC_BF16) return fail(c, PBG_ERR_INVALID, "unknown precision %d", precision);
+  if (stage_slots < 0 || stage_slots > 2) return fail(c, PBG_ERR_INVALID, "reserve: stage_slots must be 0, 1 or 2");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  const long long chunk = std::min<long long>(rows, kMaxChunk);
+  PBG_TRY(ensure_ws(c, precision, chunk, nullptr));
+  for (int i = 0; i < stage_slots; ++i) PBG_TRY(ensure_stage(c, c->stage[i], chunk, nullptr));
+  return PBG_OK;
+}
+
+int pbg_stage_triplets(pbg_ctx* c, int slot, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                       const int64_t* triplets, const float* z, int64_t B, int want_gen, int want_disc, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (slot < 0 || slot > 1) return fail(c, PBG_ERR_INVALID, "stage: slot must be 0 or 1");
+  if (B <= 0 || B > kMaxChunk) return fail(c, PBG_ERR_INVALID, "stage: B must be in [1, %lld]", kMaxChunk);
+  if (!node_emb || !rel_emb || !triplets) return fail(c, PBG_ERR_INVALID, "null tensor");
+  if (!want_gen && !want_disc) return fail(c, PBG_ERR_INVALID, "stage: nothing to stage");
+  if (want_gen && !c->g_loaded) return fail(c, PBG_ERR_NOT_LOADED, "generator weights not loaded");
+  if (want_disc && !c->d_loaded) return fail(c, PBG_ERR_NOT_LOADED, "discriminator weights not loaded");
+  if (want_gen && !z) return fail(c, PBG_ERR_INVALID, "generator needs latents z");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  StageSlot& st = c->stage[slot];
+  PBG_TRY(ensure_stage(c, st, B, s));
+  const long long* t = (const long long*)triplets;
+  StageParams sp{};
+  GatherParams& gp = sp.g;
+  gp.node_emb = node_emb; gp.rel_emb = rel_emb; gp.N = N; gp.R = R; gp.E = c->dims.embed_dim; gp.Z = c->dims.noise_dim;
+  gp.heads = t; gp.rels = t + 1; gp.tails = t + 2; gp.head_stride = gp.rel_stride = gp.tail_stride = 3;
+  gp.z = z;
+  gp.xg = want_gen ? st.xg0 : nullptr; gp.ldg = c->kg0p;
+  gp.xd = want_disc ? st.xd0 : nullptr; gp.ldd = c->kd0p;
+  gp.B = B; gp.err_flag = c->err_flag;
+  sp.xt = want_gen ? st.xt : nullptr;
+  const int blocks = (int)std::min<long long>((B + 3) / 4, (long long)c->num_sms * 16);
+  { LaunchScope ls(c, PBG_K_GATHER, s);
+    stage_rows_kernel<<<blocks, 128, 0, s>>>(sp); }
+  PBG_CUDA(c, cudaGetLastError());
+  st.B = B; st.has_g = want_gen != 0; st.has_d = want_disc != 0;
+  return PBG_OK;
+}
+
+int pbg_score_staged(pbg_ctx* c, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits, float* probs,
+                     void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (slot < 0 || slot > 1) return fail(c, PBG_ERR_INVALID, "score_staged: slot must be 0 or 1");
+  const StageSlot& st = c->stage[slot];
+  if (st.B <= 0) return fail(c, PBG_ERR_INVALID, "score_staged: nothing staged in slot %d", slot);
+  Pass a;
+  a.gen_out = gen_out; a.out_dtype = out_dtype; a.gen_scores = gen_scores; a.logits = logits; a.probs = probs;
+  a.run_g = (gen_out != nullptr || gen_scores != nullptr); a.run_d = (logits != nullptr);
+  if (a.run_g && !st.has_g) return fail(c, PBG_ERR_INVALID, "score_staged: slot %d holds no generator operands", slot);
+  if (a.run_d && !st.has_d) return fail(c, PBG_ERR_INVALID, "score_staged: slot %d holds no discriminator operands", slot);
+  if (!a.run_g && !a.run_d) return PBG_OK;
+  a.B = st.B; a.prec = PBG_PREC_BF16; a.stream = (cudaStream_t)stream;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  PBG_TRY(ensure_ws(c, PBG_PREC_BF16, st.B, a.stream));
+  GatherParams gp{};
+  return launch_pass2(c, c->ws_bf16, a, gp, 0, st.B, gen_out, gen_scores, true, &st);
 }
 
 int pbg_linear_bf16(pbg_ctx* c, int model, int layer, const void* a, void* out, int64_t M, void* stream) {

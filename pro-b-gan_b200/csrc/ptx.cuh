@@ -41,16 +41,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint of a blocking wait: the hardware parks the thread until the phase completes or this many
+// nanoseconds pass.  Without a hint the limit is short, and eight epilogue warps that wait for an accumulator then
+// re-issue try_wait in a tight loop -- on the issue slots the MMA issuer and the TMA producer (the lowest warp ids,
+// last in the scheduler's priority order) need: the r1 capture counted 1.16 M warp-level try_wait per launch.
+#ifndef PBG_TRY_WAIT_HINT_NS
+#define PBG_TRY_WAIT_HINT_NS 10000000
+#endif
+constexpr uint32_t kTryWaitHintNs = PBG_TRY_WAIT_HINT_NS;
+// hang guard: rounds of try_wait before a wait traps (a round may last up to the hint; several seconds in total)
+constexpr uint32_t kGuardSpins = kTryWaitHintNs >= 1000000u ? 4000u : 4000000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kTryWaitHintNs)
       : "memory");
   return ok != 0;
 }
@@ -85,7 +95,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if PBG_HANG_GUARD
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 4000000u) pbg_wait_timed_out("mbarrier (parity, offset)", parity, smem_u32(bar) & 0x3ffu);
+    if (++spins > kGuardSpins) pbg_wait_timed_out("mbarrier (parity, offset)", parity, smem_u32(bar) & 0x3ffu);
   }
 #else
   while (!mbar_try_wait(bar, parity)) {

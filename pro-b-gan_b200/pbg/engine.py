@@ -281,6 +281,71 @@ class Engine:
             res["logits"], res["probs"] = logits, probs
         return res
 
+    # ------------------------------------------------------------------ staged requests (ingest / compute split)
+    def reserve(self, rows: int, precision=None, stage_slots: int = 0) -> None:
+        """Size the workspaces (and staging slots) for `rows` rows up front (include/pbg.h: pbg_reserve): nothing then
+        grows -- no device synchronisation -- inside a steady-state loop or a CUDA-graph capture."""
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_reserve(self._h, int(rows), precision_code(precision), int(stage_slots)), self._h)
+
+    def stage_triplets(self, slot: int, node_emb, rel_w, triplets, z=None, want_gen=True, want_disc=True) -> int:
+        """Gather + concat + cast one request's rows into staging slot `slot` on the CURRENT stream (the caller's ingest
+        stream), beside whatever pass is running.  Returns the request's row count.  See pbg_stage_triplets."""
+        node_emb = self._f32(node_emb, self.E, "node_emb")
+        rel_w = self._f32(rel_w, self.E, "rel_emb.weight")
+        trip = self._i64(triplets, "triplets")
+        if trip.dim() != 2 or trip.shape[1] != 3:
+            raise ValueError(f"triplets must be [B, 3], got {tuple(trip.shape)}")
+        trip = trip.contiguous()
+        if want_gen:
+            if z is None:
+                raise ValueError("generator pass needs latents z")
+            z = self._f32(z, self.Z, "z")
+        B = trip.shape[0]
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_stage_triplets(
+                self._h, int(slot), _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(trip),
+                _ptr(z if want_gen else None), B, 1 if want_gen else 0, 1 if want_disc else 0, self._stream()), self._h)
+        if not hasattr(self, "_staged_rows"):
+            self._staged_rows = {}
+        self._staged_rows[int(slot)] = B
+        return B
+
+    def score_staged(self, slot: int, want_gen_out=False, want_gen_scores=False, want_disc=True,
+                     out_dtype=torch.float32, out: dict | None = None):
+        """The G + D pass over a staged request on the CURRENT stream (the compute stream); the caller has ordered it
+        after the slot's stage_triplets.  Same result dict as score_triplets (bf16 mode)."""
+        res, out = {}, (out or {})
+        B = getattr(self, "_staged_rows", {}).get(int(slot))
+        if B is None:
+            raise ValueError(f"nothing staged in slot {slot}")
+
+        def buf(key, want, shape, dtype):
+            if not want:
+                return None
+            t = out.get(key)
+            if t is None:
+                return torch.empty(shape, dtype=dtype, device=self.device)
+            if tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device or not t.is_contiguous():
+                raise ValueError(f"out[{key!r}] must be a contiguous {dtype} tensor of shape {tuple(shape)} on {self.device}")
+            return t
+
+        gen_out = buf("gen_out", want_gen_out, (B, self.E), out_dtype)
+        scores = buf("gen_scores", want_gen_scores, (B,), torch.float32)
+        logits = buf("logits", want_disc, (B,), torch.float32)
+        probs = buf("probs", want_disc, (B,), torch.float32)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_score_staged(
+                self._h, int(slot), _ptr(gen_out), cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32,
+                _ptr(scores), _ptr(logits), _ptr(probs), self._stream()), self._h)
+        if want_gen_out:
+            res["gen_out"] = gen_out
+        if want_gen_scores:
+            res["gen_scores"] = scores
+        if want_disc:
+            res["logits"], res["probs"] = logits, probs
+        return res
+
     def score_triplets_host(self, node_emb, rel_w, triplets_host, z_host=None, gen_out_host=None,
                             gen_scores_host=None, logits_host=None, probs_host=None, precision=None) -> None:
         """End-to-end form: index / latent / result buffers are HOST tensors (ideally pinned); the H2D and

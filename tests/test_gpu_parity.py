@@ -401,3 +401,140 @@ def test_wide_model_config5_matches_oracle(synth, dev):
     assert rel_err(res["logits"].cpu(), d) <= BF16_REL
     assert (res["probs"].cpu() - torch.sigmoid(d)).abs().max().item() <= BF16_REL
     assert (res["gen_scores"].cpu() - cs).abs().max().item() <= BF16_REL
+
+
+# ----------------------------------------------------------------------------- staged requests (ingest / compute split)
+@pytest.mark.parametrize("B", [1, 100, 4096, 5000])
+def test_staged_request_equals_the_fused_pass_bit_for_bit(engine, dev_tables, synth, dev, B):
+    """pbg_stage_triplets on an ingest stream + pbg_score_staged on the compute stream = pbg_score_triplets: the staging
+    kernel copies the same rows with the same single bf16 rounding, the pass is the same kernel (gather phase off)."""
+    trip, z = synth.make_triplets(B, seed=77).to(dev), synth.make_latents(B, seed=78).to(dev)
+    ref = {k: v.clone() for k, v in _pass(engine, dev_tables, trip, z).items()}
+    ingest = torch.cuda.Stream(dev)
+    for slot in (0, 1):
+        ingest.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(ingest):
+            assert engine.stage_triplets(slot, *dev_tables, trip, z) == B
+        torch.cuda.current_stream(dev).wait_stream(ingest)
+        res = engine.score_staged(slot, want_gen_out=True, want_gen_scores=True, want_disc=True, out_dtype=torch.bfloat16)
+        engine.check_indices()
+        for k in ref:
+            assert torch.equal(res[k], ref[k]), f"slot {slot}: {k} differs"
+
+
+def test_staged_pipeline_in_a_cuda_graph_with_two_slots(cuda_models, dev_tables, synth, dev):
+    """bench.py's lane: request j + 1 staged on the ingest stream while pass j runs, two slots, the whole sequence
+    captured into one CUDA graph (pbg_reserve first: nothing may grow during capture) and replayed."""
+    import modular_prot_b_gan as m
+    B, n = 1000, 6
+    eng = m.make_fused_engine(*cuda_models, ctas=48)
+    inputs = [(synth.make_triplets(B, seed=300 + i).to(dev), synth.make_latents(B, seed=400 + i).to(dev)) for i in range(n)]
+    ref = [{k: v.clone() for k, v in _pass(eng, dev_tables, t, z).items()} for t, z in inputs]
+    outs = [{"gen_out": torch.zeros(B, 128, dtype=torch.bfloat16, device=dev), "gen_scores": torch.zeros(B, device=dev),
+             "logits": torch.zeros(B, device=dev), "probs": torch.zeros(B, device=dev)} for _ in range(n)]
+    fresh = m.make_fused_engine(*cuda_models, ctas=48)
+    cs, ins = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(cs):
+        with pytest.raises(Exception):          # growth inside a capture is refused, not a device-wide sync
+            with torch.cuda.graph(torch.cuda.CUDAGraph(), stream=cs):
+                fresh.stage_triplets(0, *dev_tables, *inputs[0])
+    torch.cuda.synchronize()
+    eng.reserve(B, "bf16", 2)
+    with torch.cuda.stream(cs):
+        with torch.cuda.graph(g, stream=cs):
+            fork = torch.cuda.Event(); fork.record(cs); ins.wait_event(fork)
+            done = [None, None]
+            for j, (t, z) in enumerate(inputs):
+                slot = j & 1
+                with torch.cuda.stream(ins):
+                    if done[slot] is not None:
+                        ins.wait_event(done[slot])
+                    eng.stage_triplets(slot, *dev_tables, t, z)
+                    staged = torch.cuda.Event(); staged.record(ins)
+                cs.wait_event(staged)
+                eng.score_staged(slot, want_gen_out=True, want_gen_scores=True, want_disc=True, out_dtype=torch.bfloat16,
+                                 out=outs[j])
+                done[slot] = torch.cuda.Event(); done[slot].record(cs)
+    for _ in range(3):
+        for o in outs:
+            for v in o.values():
+                v.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(cs):
+            g.replay()
+        torch.cuda.synchronize()
+        for j in range(n):
+            for k in ref[j]:
+                assert torch.equal(outs[j][k], ref[j][k]), f"request {j}: {k} differs"
+    eng.check_indices()
+
+
+def test_staged_request_flags_bad_ids_and_misuse(engine, dev_tables, synth, dev):
+    B = 64
+    z = synth.make_latents(B).to(dev)
+    for col, bad in ((0, 65536), (1, -1), (2, -65537)):
+        trip = synth.make_triplets(B).to(dev)
+        trip[5, col] = bad
+        engine.stage_triplets(0, *dev_tables, trip, z)
+        engine.score_staged(0, want_disc=True)
+        with pytest.raises(IndexError):
+            engine.check_indices()
+    trip = synth.make_triplets(B).to(dev)
+    engine.stage_triplets(1, *dev_tables, trip, None, want_gen=False, want_disc=True)
+    with pytest.raises(Exception):
+        engine.score_staged(1, want_gen_out=True)           # no generator operands in the slot
+    assert engine.score_staged(1, want_disc=True)["logits"].shape == (B,)
+    engine.check_indices()
+
+
+def test_generator_only_pass_still_validates_tail_ids(engine, dev_tables, synth, dev):
+    """with no discriminator operand built nothing used to look at the tails; the reference raises
+    IndexError at node_emb[tails] (pro_b_gan_infer.py:188) for every method."""
+    B, N = 40, 65536
+    z = synth.make_latents(B).to(dev)
+    for prec in ("fp32", "bf16"):
+        for bad in (N, -N - 1):
+            trip = synth.make_triplets(B).to(dev)
+            trip[7, 2] = bad
+            engine.score_triplets(*dev_tables, trip, z, want_gen_scores=True, want_disc=False, precision=prec)
+            with pytest.raises(IndexError):
+                engine.check_indices()
+        trip = synth.make_triplets(B).to(dev)
+        trip[7, 2] = -1                                      # wraps to the last row, like tensor indexing
+        a = engine.score_triplets(*dev_tables, trip, z, want_gen_scores=True, want_disc=False, precision=prec)
+        trip[7, 2] = N - 1
+        b = engine.score_triplets(*dev_tables, trip, z, want_gen_scores=True, want_disc=False, precision=prec)
+        engine.check_indices()
+        assert torch.equal(a["gen_scores"], b["gen_scores"])
+
+
+# ----------------------------------------------------------------------------- stress: the relaxed layer hand-off
+def test_stress_ragged_sizes_on_concurrent_lanes_bit_identical(cuda_models, dev_tables, synth, dev):
+    """>= 200 passes over ragged batch sizes on 3 concurrent lanes (48 SMs each, as bench.py runs them), every result
+    compared bit for bit with the first run of its inputs: the activation hand-off (bulk-store completion + relaxed
+    counter increment, consumer's relaxed poll + proxy fence) has no other check than this -- a missed
+    dependency shows as a mismatch, a lost arrival as a hang (the in-kernel guard traps)."""
+    import modular_prot_b_gan as m
+    S = 3
+    sizes = [1, 31, 255, 256, 257, 1000, 4096, 5000, 9000]
+    engines = [m.make_fused_engine(*cuda_models, ctas=48) for _ in range(S)]
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    inputs = [(synth.make_triplets(B, seed=500 + i).to(dev), synth.make_latents(B, seed=600 + i).to(dev)) for i, B in enumerate(sizes)]
+    ref = [{k: v.clone() for k, v in _pass(engines[0], dev_tables, t, z).items()} for t, z in inputs]
+    torch.cuda.synchronize()
+    n = 0
+    for rep in range(8):
+        got = []
+        for i in range(3 * len(sizes)):
+            j = (i * 7 + rep) % len(sizes)
+            with torch.cuda.stream(streams[i % S]):
+                got.append((j, _pass(engines[i % S], dev_tables, *inputs[j])))
+        torch.cuda.synchronize()
+        for j, res in got:
+            n += 1
+            for k in ref[j]:
+                assert torch.equal(res[k], ref[j][k]), f"rep {rep}, B = {sizes[j]}: {k} differs"
+    for e in engines:
+        e.check_indices()
+    assert n >= 200

@@ -29,9 +29,15 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
     outb = {"gen_out": torch.empty(B, 128, dtype=torch.bfloat16, device=dev), "gen_scores": torch.empty(B, device=dev),
             "logits": torch.empty(B, device=dev), "probs": torch.empty(B, device=dev)}
 
+    STAGED = int(os.environ.get("TRACE_STAGED", "0"))   # 1: the rows are staged by pbg_stage_triplets (gather phase off)
+
     def run():
-        eng.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
-                           precision="bf16", out_dtype=torch.bfloat16, out=outb)
+        if STAGED:
+            eng.stage_triplets(0, node_emb, rel_w, trip, z)
+            eng.score_staged(0, want_gen_out=True, want_gen_scores=True, want_disc=True, out_dtype=torch.bfloat16, out=outb)
+        else:
+            eng.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
+                               precision="bf16", out_dtype=torch.bfloat16, out=outb)
     for _ in range(5):
         run()
     torch.cuda.synchronize()
@@ -98,15 +104,15 @@ for B in [int(x) for x in (sys.argv[1:] or ["4096"])]:
         dep = items[:, :, 1][sel]; accr = items[:, :, 2][sel]; done = items[:, :, 3][sel]
         c0s = c0.expand(-1, 56)[sel]
         depw = torch.where(dep > 0, dep - c0s - cl, torch.zeros_like(dep))
-        P(f"   {name}: n={int(sel.sum()):5d} claim@ {cl.mean():8.0f} (min {cl.min():.0f} max {cl.max():.0f})  dep-wait {depw.mean():7.0f} (max {depw.max():.0f})"
+        P(f"   {name}: n={int(sel.sum()):5d} claim@ {cl.mean():8.0f} (min {cl.min():.0f} max {cl.max():.0f})  claim->mma0 {depw.mean():7.0f} (max {depw.max():.0f})"
           f"  claim->acc {((accr - c0s) - cl).mean():7.0f}  epilogue {(done - accr).mean():6.0f} (max {(done - accr).max():.0f})  done@ max {(done - c0s).max():.0f}")
     if B <= 4096:
-        for cta in (0, 20, 46) if CTAS else (0, 60, 140):
+        for cta in (0, 1, 10, 20, 30, 46) if CTAS else (0, 60, 140):
             if cta >= t.shape[0]:
                 continue
             rows = []
             for i in range(56):
                 if not valid[cta, i]:
                     break
-                rows.append(f"{KIND[int(kind[cta, i])]}[m{int(mblk[cta, i])}] claim {claim_r[cta, i]:.0f} dep {max(items[cta, i, 1] - c0[cta, 0], 0):.0f} acc {items[cta, i, 2] - c0[cta, 0]:.0f} done {items[cta, i, 3] - c0[cta, 0]:.0f}")
-            P(f"   CTA {cta}: " + " | ".join(rows))
+                rows.append(f"{KIND[int(kind[cta, i])]}[m{int(mblk[cta, i])}] claim {claim_r[cta, i]:.0f} mma0 {max(items[cta, i, 1] - c0[cta, 0], 0):.0f} acc {items[cta, i, 2] - c0[cta, 0]:.0f} done {items[cta, i, 3] - c0[cta, 0]:.0f}")
+            P(f"   CTA {cta} (end {hdr[cta, 8] - hdr[cta, 0]:.0f}): " + " | ".join(rows))
