@@ -111,7 +111,7 @@ class ModularDiscriminator(nn.Module):
 
 
 # The script's globals must contain these two names when ProtBGANInference.__init__
-# runs (pro_b_gan_infer.py:93-94); see oracle/run_reference.py for the injection.
+# runs (pro_b_gan_infer.py:93-94); pro-b-gan_b200/pbg/launcher.py and tests/golden/make_golden.py do the injection.
 Generator = ModularGenerator
 Discriminator = ModularDiscriminator
 

@@ -543,7 +543,6 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.probs = a.probs ? a.probs + off : nullptr;
   p.part_d = w.part_d; p.slots_d = on[IT_D_L1] ? lin[IT_D_L1]->np / 64 : 0;
   p.trace = c->trace;
-  { static const int dbg_env = [] { const char* e = getenv("PBG_DBG"); return e ? atoi(e) : 0; }(); p.dbg = dbg_env; }
   p.n_mirror = c->n_mirror;
   for (int i = 0; i < c->n_mirror; ++i) {
     if (gen_out && !c->mir_gen[i]) return fail(c, PBG_ERR_INVALID, "result mirror %d has no gen_out buffer", i);

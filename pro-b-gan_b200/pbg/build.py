@@ -54,5 +54,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_variant(tag: str, defines: list[str]) -> Path:
+    """A/B builds for same-box comparisons: libpbg_b200.<tag>.so with extra -D flags; select with PBG_LIB_PATH."""
+    nvcc = find_nvcc()
+    out = PKG_DIR / f"libpbg_b200.{tag}.so"
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], f"-I{INCLUDE}", "-o", str(out), str(CSRC / "pbg.cu")]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed building {out.name}")
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--variant" in sys.argv:   # python -m pbg.build --variant TAG DEFINE[=V] ...
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -50,7 +50,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build()
+    import os
+    override = os.environ.get("PBG_LIB_PATH")     # an A/B build of the same sources (pbg.build --variant), never a fallback
+    path = Path(override) if override else _build.build()
     lib = C.CDLL(str(path))
     vp, i64, i32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_size_t
     sig = {
