@@ -309,32 +309,38 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     lo, hi = shard.shard_bounds(Bg, world, rank)
     # one contiguous result block per pool entry and rank: [gen_out bf16 B x E | scores | logits | probs fp32 B each].
     # N > 1: the blocks of all ranks for one step form that step's assembled output [world, block] on EVERY rank.
-    #   exchange "p2p"  (default): the buffers live in symmetric memory and every pass writes its rows straight into
-    #                   the peers' copies from the kernel epilogues (result mirrors, NVLink stores; no collective)
+    #   exchange "mc"   (default): the buffers live in symmetric memory with an NVSwitch multicast mapping and every
+    #                   pass writes its rows ONCE, with multimem.st from its epilogues; the switch replicates them into
+    #                   every GPU's copy (result multicast; no collective, NVLink egress = one copy of the rows)
+    #   exchange "p2p": the same buffers, one unicast store per peer from the epilogues (result mirrors) -- also the
+    #                   fallback when the box offers no multicast mapping
     #   exchange "nccl": one all-gather of the block per step on a per-lane communicator (eager, no graphs)
     blk_bytes = B * (2 * E + 12)
     exchange = "none"
-    peer_ptrs = None
+    peer_ptrs, mc_ptr = None, 0
     if world > 1:
         exchange = args.exchange
-        if exchange == "p2p":
+        if exchange in ("p2p", "mc"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 sym = symm_mem.empty(P * world * blk_bytes, dtype=torch.uint8, device=dev)
                 hdl = symm_mem.rendezvous(sym, dist.group.WORLD)
                 peer_ptrs = [int(x) for x in hdl.buffer_ptrs]
+                mc_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
             except Exception as ex:  # symmetric memory unavailable on this box: fall back to the collective
                 if rank == 0:
                     print(f"bench.py: symmetric memory unavailable ({ex}); using the NCCL all-gather", file=sys.stderr)
                 exchange = "nccl"
-        # every rank must take the same path
-        flag = torch.tensor([1 if exchange == "p2p" else 0], device=dev)
+        # every rank must take the same path: multicast > unicast mirrors > NCCL all-gather
+        level = {"mc": 2 if mc_ptr else 1, "p2p": 1, "nccl": 0}[exchange]
+        flag = torch.tensor([level], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            exchange, peer_ptrs = "nccl", None
-    if exchange != "p2p":
+        exchange = ("nccl", "p2p", "mc")[int(flag.item())]
+        if exchange == "nccl":
+            peer_ptrs = None
+    if exchange not in ("p2p", "mc"):
         sym = torch.empty(P * max(world, 1) * blk_bytes, dtype=torch.uint8, device=dev)
-    pool, mirrors = [], []
+    pool, mirrors, mcasts = [], [], []
     for i in range(P):
         trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=4321 + i)[lo:hi].contiguous().to(dev)
         z = synth.make_latents(Bg, Z, seed=1234 + i)[lo:hi].contiguous().to(dev)
@@ -349,6 +355,9 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
             base = [peer_ptrs[r] + off for r in range(world) if r != rank]
             mirrors.append({"gen_out": base, "gen_scores": [b + B * 2 * E for b in base],
                             "logits": [b + B * 2 * E + 4 * B for b in base], "probs": [b + B * 2 * E + 8 * B for b in base]})
+        if exchange == "mc":
+            b = mc_ptr + off
+            mcasts.append({"gen_out": b, "gen_scores": b + B * 2 * E, "logits": b + B * 2 * E + 4 * B, "probs": b + B * 2 * E + 8 * B})
     lane_pg = None
     if exchange == "nccl":
         # one communicator per lane: collectives of different lanes run on different streams, and NCCL requires the
@@ -366,6 +375,8 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
                     trip, z, out = pool[e]
                     if exchange == "p2p":
                         eng.set_result_mirrors(**mirrors[e])
+                    if exchange == "mc":
+                        eng.set_result_multicast(**mcasts[e])
                     eng.score_triplets(node_emb, rel_w, trip, z, precision="bf16", out=out, **kw)
                     if exchange == "nccl":  # reassemble the outputs on every rank (north_star: NVLink all-gather)
                         dist.all_gather_into_tensor(out["assembled"], out["block"], group=lane_pg[l])
@@ -386,6 +397,8 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
                 cs.wait_event(staged)
                 if exchange == "p2p":
                     eng.set_result_mirrors(**mirrors[e])
+                if exchange == "mc":
+                    eng.set_result_multicast(**mcasts[e])
                 eng.score_staged(slot, out=out, **kw)
                 if exchange == "nccl":
                     dist.all_gather_into_tensor(out["assembled"], out["block"], group=lane_pg[l])
@@ -524,6 +537,7 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     T = args.e2e_threads if args.e2e_threads > 0 else S
     for e in engines:
         e.set_result_mirrors()   # host results need no re-assembly: every rank's caller receives its own shard
+        e.set_result_multicast()
     e2e_engines = engines + [m.make_fused_engine(G, D, ctas=widths[i % S]) for i in range(max(0, T - S))]
     h_out = [(None, torch.empty(B).pin_memory(), torch.empty(B).pin_memory(), torch.empty(B).pin_memory())
              for _ in range(T)]  # score_triplets returns scores / logits / probabilities, not the predicted embeddings
@@ -566,8 +580,6 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     peaks = measured_peaks()
     for e in engines:
         e.profile_enable(True); e.profile_read()
-    if exchange == "p2p":
-        pass  # mirrors are set per step inside lane_run
     ev = torch.cuda.Event(); ev.record(main)
     for s in cstreams:
         s.wait_event(ev)
@@ -581,12 +593,20 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
             a[0] += v[0]; a[1] += v[1]
         e.profile_enable(False)
         e.set_result_mirrors()
+        e.set_result_multicast()
     flops = {"pass": B * FLOP_SAMPLE}  # the fused kernel runs the whole G + D pass
     kinds = {k: {"ms_per_launch": v[0] / v[1], "launches": v[1]} for k, v in prof.items() if v[1] > 0}
     dom = "pass"
     ach = flops[dom] / (kinds[dom]["ms_per_launch"] * 1e-3) / 1e12
     step_tflops = FLOP_SAMPLE * value / world / 1e12
-    peak = peaks["bf16_burst"]
+    # Denominator (B200_PROFILING.md: "the burst figure for a kernel timed alone, the sustained one for a kernel timed
+    # inside a long step"): the timed region is >= 50 ms of back-to-back passes, repeated; when NVML reports the power
+    # cap during it (SM clocks below the maximum) the sustained cuBLAS figure is the like-for-like peak, otherwise the
+    # burst one.  Both fractions are always printed.
+    clock_summary = clk.summary()
+    capped = "sw_power_cap" in (clock_summary.get("reasons") or [])
+    use_sustained = capped and ms_med >= 25.0
+    peak = peaks["bf16_sustained"] if use_sustained else peaks["bf16_burst"]
     ctas_avg = sum((w if w > 0 else num_sms) for w in widths) / len(widths)
     share = ctas_avg / num_sms
     traffic, traffic_src = None, None
@@ -597,13 +617,17 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
         traffic_src = tj.get("source")
     roofline = {"bound": "tensor", "kernel": dom, "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": step_tflops / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peaks["source"] + ", burst figure (cuBLAS bf16 8192^3, best of 10); frac_of_sustained beside it",
+                "peak_source": peaks["source"] + (", SUSTAINED figure (cuBLAS bf16 back to back for seconds under the power cap): this "
+                                                  f"timed region is {ms_med:.0f} ms x {len(trials)} trials and NVML reported sw_power_cap during it"
+                                                  if use_sustained else ", burst figure (cuBLAS bf16 8192^3, best of 10)"),
+                "frac_of_burst": step_tflops / peaks["bf16_burst"], "frac_of_sustained": step_tflops / peaks["bf16_sustained"],
+                "best_trial_frac_of_burst": FLOP_SAMPLE * (Bg * n_timed / (ms_best * 1e-3)) / world / 1e12 / peaks["bf16_burst"],
                 "note": f"achieved = algorithmic flops per sample x measured throughput of the timed region (median "
                         f"trial) = flops of the launches in flight / their average duration x overlap; one launch "
                         f"alone: see per_launch (it occupies {ctas_avg:.0f} of {num_sms} SMs)",
                 "flops_per_launch": flops[dom], "us_per_launch": kinds[dom]["ms_per_launch"] * 1e3,
                 "per_launch": {"achieved": ach, "sm_share": share, "peak_share": peak * share, "frac_of_share": ach / (peak * share)},
-                "whole_step": {"achieved": step_tflops, "frac": step_tflops / peak,
+                "whole_step": {"achieved": step_tflops, "frac": step_tflops / peaks["bf16_burst"],
                                "frac_of_sustained": step_tflops / peaks["bf16_sustained"],
                                "flops_per_sample": FLOP_SAMPLE},
                 "per_kernel_us": {k: round(v["ms_per_launch"] * 1e3, 3) for k, v in kinds.items()}}
@@ -633,9 +657,11 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
                        "lanes": S, "ctas_per_pass": [w if w > 0 else num_sms for w in widths[:min(S, 3)]],
                        "stage_ahead": stage_ahead,
                        "collective": {"none": "none", "p2p": "none: every pass writes its result rows into all peers' symmetric-memory "
-                                      "windows from its epilogues (NVLink stores)", "nccl": "all-gather of outputs (NCCL, "
-                                      "one per step)"}[exchange]},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
+                                      "windows from its epilogues (NVLink stores, one per peer)",
+                                      "mc": "none: every pass writes its result rows once, with multimem.st to the NVSwitch multicast "
+                                            "address of the symmetric result buffers, from its epilogues",
+                                      "nccl": "all-gather of outputs (NCCL, one per step)"}[exchange]},
+            "clocks": clock_summary, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline,
             "cpu_baseline": cpu, "gpu_library_baseline": lib,
         }
         if exchange_check is not None:
@@ -656,8 +682,9 @@ def main() -> None:
     ap.add_argument("--per-gpu-batch", "--batch", dest="batch", type=int, default=0, help="triplets per GPU per step (0: the config's)")
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=6, help="independent requests in flight (one ctx + compute/ingest stream each)")
-    ap.add_argument("--stage-ahead", type=int, default=1, help="1: the next request of a lane is staged while the current pass runs")
-    ap.add_argument("--exchange", choices=["p2p", "nccl"], default="p2p", help="N > 1: how the outputs are re-assembled")
+    ap.add_argument("--stage-ahead", type=int, default=0, help="1: the next request of a lane is staged (pbg_stage_triplets) on an "
+                    "ingest stream while the current pass runs; 0 (default, measured 3 %% faster in steady state): gather inside the pass")
+    ap.add_argument("--exchange", choices=["mc", "p2p", "nccl"], default="mc", help="N > 1: how the outputs are re-assembled")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads of the e2e leg (0: one per lane)")
     ap.add_argument("--e2e-min-s", type=float, default=0.4, help="the e2e leg runs at least this long (and >= --steps calls)")
     ap.add_argument("--ctas", type=int, default=0, help="SMs per pass (0: 50 / 50 / 48 of 148, whole CTA pairs)")

@@ -212,6 +212,15 @@ int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
 int pbg_set_result_mirrors(pbg_ctx* ctx, int n, void* const* gen_out, float* const* gen_scores,
                            float* const* logits, float* const* probs);
 
+/* Result multicast -- the same exchange through ONE store per 16 bytes instead of one per peer.  The four pointers are
+ * NVSwitch multicast addresses (cuMulticast* objects; torch symmetric memory: handle.multicast_ptr) of symmetric result
+ * buffers, already offset to the caller's shard; a NULL pointer leaves that result out; all NULL clears.  Every bf16-mode
+ * pass then ALSO writes each result row with multimem.st to the multicast address, and the switch replicates the store
+ * into every GPU's copy of the buffer (the caller's own copy included): NVLink egress per GPU is one copy of its
+ * rows whatever the number of GPUs.  Completion and reader synchronisation as for mirrors.  The addresses must really
+ * be multicast mappings: multimem.st to ordinary memory faults. */
+int pbg_set_result_multicast(pbg_ctx* ctx, void* gen_out_mc, float* gen_scores_mc, float* logits_mc, float* probs_mc);
+
 /* Entity scoring + top-k: the tail of ProtBGANInference.predict_tails (pro_b_gan_infer.py:146-151) and all of
  * find_similar_entities (:231-236):
  *     similarities = F.normalize(queries, dim=-1) @ F.normalize(table, dim=-1).T      [B, N], never materialised

@@ -111,6 +111,9 @@ struct alignas(64) Pass2Params {
   // the output all-gather of a batch-sharded job without a collective; pbg_set_result_mirrors)
   int n_mirror;
   void* mir_gen[kMaxMirrors]; float* mir_cos[kMaxMirrors]; float* mir_logits[kMaxMirrors]; float* mir_probs[kMaxMirrors];
+  // result multicast: NVSwitch multicast addresses of the same result buffers (pbg_set_result_multicast): one
+  // multimem.st per 16 bytes leaves this GPU and the switch replicates it into every GPU's copy
+  void* mc_gen; float* mc_cos; float* mc_logits; float* mc_probs;
   long long* trace;
 };
 static_assert(sizeof(Pass2Params) <= 4096, "kernel parameter space");
@@ -132,6 +135,14 @@ static_assert(P2Smem::kTotal <= 232448, "pass2: shared memory budget");
 
 __device__ __forceinline__ void st_cluster_u32x2(uint32_t cluster_addr, uint2 v) {
   asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y) : "memory");
+}
+// Stores to an NVSwitch multicast address: every replica (one per GPU of the multicast group) receives the value.
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+__device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   float2 d;
@@ -788,6 +799,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 p.mir_logits[mi][gr] = logit;
                 if (p.mir_probs[mi] != nullptr) p.mir_probs[mi][gr] = prob;
               }
+              if (p.mc_logits != nullptr) multimem_st_f32(p.mc_logits + gr, logit);
+              if (p.mc_probs != nullptr) multimem_st_f32(p.mc_probs + gr, prob);
             }
           }
         }
@@ -848,6 +861,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                   const float cs = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
                   p.cosine[grow] = cs;
                   for (int mi = 0; mi < p.n_mirror; ++mi) p.mir_cos[mi][grow] = cs;
+                  if (p.mc_cos != nullptr) multimem_st_f32(p.mc_cos + grow, cs);
                 }
               }
               asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the slot may be rewritten after this
@@ -889,6 +903,27 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                   w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
                   w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
                   if (col0 + t * 8 < p.n_valid) *reinterpret_cast<uint4*>(orow + t * 8) = w;
+                }
+              }
+            }
+            if (p.mc_gen != nullptr) {   // uncommon shapes (fp32 output, E != 128): 16-byte multicast stores from registers
+              if (p.out_f32) {
+                char* orow = static_cast<char*>(p.mc_gen) + (static_cast<size_t>(grow) * p.ld_gen + col0) * 4;
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                  if (col0 + t * 4 < p.n_valid)
+                    multimem_st_v4(orow + t * 16, make_uint4(__float_as_uint(f[4 * t]), __float_as_uint(f[4 * t + 1]),
+                                                             __float_as_uint(f[4 * t + 2]), __float_as_uint(f[4 * t + 3])));
+              } else {
+                char* orow = static_cast<char*>(p.mc_gen) + (static_cast<size_t>(grow) * p.ld_gen + col0) * 2;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  uint4 w;
+                  w.x = pack_bf16x2(f[8 * t + 0], f[8 * t + 1]);
+                  w.y = pack_bf16x2(f[8 * t + 2], f[8 * t + 3]);
+                  w.z = pack_bf16x2(f[8 * t + 4], f[8 * t + 5]);
+                  w.w = pack_bf16x2(f[8 * t + 6], f[8 * t + 7]);
+                  if (col0 + t * 8 < p.n_valid) multimem_st_v4(orow + t * 16, w);
                 }
               }
             }
@@ -945,6 +980,18 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 tma_store_commit();
               }
             }
+            if (p.mc_gen != nullptr) {
+              // multi-GPU: the same 8 KB leave once through the multicast address, 16 bytes per thread and store, 512
+              // contiguous bytes per warp instruction; NVSwitch writes them into every GPU's copy of the buffer
+              const long long row0 = grow - lane;
+              const int nbytes = static_cast<int>(min(32ll, p.M - row0)) * 256;
+              char* dst = static_cast<char*>(p.mc_gen) + row0 * 256;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int off = (i * 64 + half * 32 + lane) * 16;
+                if (off < nbytes) multimem_st_v4(dst + off, *reinterpret_cast<const uint4*>(region + off));
+              }
+            }
             // The bulk engine is still reading the region (one 8 KB read per destination: the caller's buffer and up to
             // seven mirrors over NVLink).  Nobody waits for that here: pair_settle() does, right before the quarter's
             // staging tiles are next written -- normally many thousand clocks later, or never (last item of the pass).
@@ -978,6 +1025,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
                 const float cs = d / (fmaxf(sqrtf(pp), 1e-8f) * fmaxf(sqrtf(tt), 1e-8f));
                 p.cosine[gr] = cs;
                 for (int mi = 0; mi < p.n_mirror; ++mi) p.mir_cos[mi][gr] = cs;
+                if (p.mc_cos != nullptr) multimem_st_f32(p.mc_cos + gr, cs);
               }
             }
           }

@@ -120,6 +120,7 @@ struct pbg_ctx {
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
   int n_mirror = 0;     // pbg_set_result_mirrors
   void* mir_gen[kMaxMirrors] = {}; float* mir_cos[kMaxMirrors] = {}; float* mir_logits[kMaxMirrors] = {}; float* mir_probs[kMaxMirrors] = {};
+  void* mc_gen = nullptr; float *mc_cos = nullptr, *mc_logits = nullptr, *mc_probs = nullptr;   // pbg_set_result_multicast
   bool profiling = false;
   long long* trace = nullptr;  // device, 16 slots x num_sms (pbg_debug_trace)
   struct ProfRec { cudaEvent_t a, b; int kind; };
@@ -372,7 +373,8 @@ int run_chunk(pbg_ctx* c, const Pass& a, long long off, long long rows) {
   gp.xd = a.run_d ? w.xd0 : nullptr; gp.ldd = bf ? c->kd0p : c->kd0;
   gp.B = rows; gp.err_flag = c->err_flag;
   const int gather_blocks = (int)std::min<long long>((rows + 7) / 8, (long long)c->num_sms * 8);
-  if (!bf && c->n_mirror > 0) return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors are a bf16-mode feature");
+  if (!bf && (c->n_mirror > 0 || c->mc_gen || c->mc_cos || c->mc_logits))
+    return fail(c, PBG_ERR_UNSUPPORTED, "result mirrors / multicast are a bf16-mode feature");
   // bf16 mode gathers inside the fused pass kernel.  PBG_SPLIT_GATHER=1 (experiment, see DESIGN.md 3.1 "time model"):
   // the rows are gathered by this small kernel instead -- it fits beside resident pass CTAs of other lanes (no shared
   // memory, few registers), so a pass no longer holds its SMs through a gather phase with idle tensor pipes.
@@ -553,6 +555,13 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     p.mir_cos[i] = c->mir_cos[i] ? c->mir_cos[i] + off : nullptr;
     p.mir_logits[i] = c->mir_logits[i] ? c->mir_logits[i] + off : nullptr;
     p.mir_probs[i] = (c->mir_probs[i] && a.probs) ? c->mir_probs[i] + off : nullptr;
+  }
+  {
+    const size_t es = a.out_dtype == PBG_DT_BF16 ? 2 : 4;
+    p.mc_gen = (c->mc_gen && gen_out) ? static_cast<char*>(c->mc_gen) + static_cast<size_t>(off) * c->dims.embed_dim * es : nullptr;
+    p.mc_cos = (c->mc_cos && scores) ? c->mc_cos + off : nullptr;
+    p.mc_logits = (c->mc_logits && a.logits) ? c->mc_logits + off : nullptr;
+    p.mc_probs = (c->mc_probs && a.probs) ? c->mc_probs + off : nullptr;
   }
   // programmatic dependent launch: this pass may begin its prologue while the previous kernel of the stream drains
   static const bool pdl = [] { const char* e = getenv("PBG_PDL"); return !e || atoi(e) != 0; }();
@@ -751,6 +760,12 @@ int pbg_set_result_mirrors(pbg_ctx* c, int n, void* const* gen_out, float* const
     c->mir_logits[i] = (i < n && logits) ? logits[i] : nullptr;
     c->mir_probs[i] = (i < n && probs) ? probs[i] : nullptr;
   }
+  return PBG_OK;
+}
+
+int pbg_set_result_multicast(pbg_ctx* c, void* gen_out_mc, float* gen_scores_mc, float* logits_mc, float* probs_mc) {
+  if (!c) return PBG_ERR_INVALID;
+  c->mc_gen = gen_out_mc; c->mc_cos = gen_scores_mc; c->mc_logits = logits_mc; c->mc_probs = probs_mc;
   return PBG_OK;
 }
 

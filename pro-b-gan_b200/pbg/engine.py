@@ -108,6 +108,12 @@ class Engine:
         cabi.check(self._lib.pbg_set_result_mirrors(self._h, n, *[C.cast(x, C.c_void_p) if x is not None else None for x in a]),
                    self._h)
 
+    def set_result_multicast(self, gen_out: int = 0, gen_scores: int = 0, logits: int = 0, probs: int = 0) -> None:
+        """NVSwitch multicast addresses (ints) of symmetric result buffers, offset to this rank's shard: every bf16-mode
+        pass also writes its rows there with multimem.st (include/pbg.h: pbg_set_result_multicast).  All 0 clears."""
+        cabi.check(self._lib.pbg_set_result_multicast(self._h, *[C.c_void_p(int(x)) if x else None
+                                                                 for x in (gen_out, gen_scores, logits, probs)]), self._h)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

@@ -32,10 +32,22 @@ f32 = mine[B * 2 * E:].view(torch.float32)
 out = {"gen_out": mine[:B * 2 * E].view(torch.bfloat16).view(B, E), "gen_scores": f32[:B], "logits": f32[B:2 * B], "probs": f32[2 * B:3 * B]}
 peers = [r for r in range(world) if r != rank]
 base = [hdl.buffer_ptrs[r] + rank * blk for r in peers]
-eng.set_result_mirrors(gen_out=base, gen_scores=[b + B * 2 * E for b in base], logits=[b + B * 2 * E + 4 * B for b in base],
-                       probs=[b + B * 2 * E + 8 * B for b in base])
+mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+modes = ["mirrors (one unicast store per peer)"] + (["multicast (multimem.st, NVSwitch replicates)"] if mc else [])
+if rank == 0:
+    print(f"world {world}: multicast mapping {'available' if mc else 'NOT available'}", flush=True)
 ok = True
-for rep in range(3):
+for mode in modes:
+  sym.zero_(); torch.cuda.synchronize(); dist.barrier()
+  if mode.startswith("mirrors"):
+    eng.set_result_multicast()
+    eng.set_result_mirrors(gen_out=base, gen_scores=[b + B * 2 * E for b in base], logits=[b + B * 2 * E + 4 * B for b in base],
+                           probs=[b + B * 2 * E + 8 * B for b in base])
+  else:
+    eng.set_result_mirrors()
+    b0 = mc + rank * blk
+    eng.set_result_multicast(gen_out=b0, gen_scores=b0 + B * 2 * E, logits=b0 + B * 2 * E + 4 * B, probs=b0 + B * 2 * E + 8 * B)
+  for rep in range(3):
     trip = synth.make_triplets(Bg, seed=4321 + rep)[lo:hi].contiguous().to(dev)
     z = synth.make_latents(Bg, seed=1234 + rep)[lo:hi].contiguous().to(dev)
     eng.score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
@@ -46,9 +58,9 @@ for rep in range(3):
     torch.cuda.synchronize()
     same = torch.equal(ref, sym)
     ok &= same
-    print(f"rank {rank} rep {rep}: assembled buffer {'matches' if same else 'DIFFERS from'} the all-gather "
+    print(f"rank {rank} {mode} rep {rep}: assembled buffer {'matches' if same else 'DIFFERS from'} the all-gather "
           f"({int((ref != sym).sum())} bytes differ), logits sum {float(out['logits'].sum()):.4f}", flush=True)
     dist.barrier()
-eng.set_result_mirrors()
+eng.set_result_mirrors(); eng.set_result_multicast()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
