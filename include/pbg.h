@@ -227,12 +227,17 @@ int pbg_set_result_multicast(pbg_ctx* ctx, void* gen_out_mc, float* gen_scores_m
  *     top_scores, top_indices = similarities.topk(k, dim=1)                           (largest first)
  * pbg_topk_prepare reads the fp32 table [N, E] once (row norms + a normalised bf16 copy; the reference re-normalises
  * all N rows on every call) -- call it again whenever the table changes.  pbg_topk scores fp32 queries [B, E] against
- * the prepared table: bf16 tensor-core scores pick 32 candidates per (row, table slice), every candidate is re-scored
- * exactly in fp32 and a row whose k-th exact score does not provably beat everything that was filtered out is redone
- * by an exact scan, so indices / scores are those of an fp32 evaluation (ties between equal scores: lower index
- * first).  out_idx int64 [B, k], out_scores fp32 [B, k]; 1 <= k <= 64 and k <= N.  Stream-ordered. */
+ * the prepared table.  E == 128 and k <= 16: bf16 tensor-core scores of a table sample give a cut-off per row, a second
+ * tensor-core pass over the whole table marks every entity above it, every marked entity is re-scored exactly in fp32
+ * and a row whose k-th exact score does not provably beat everything that was not marked is redone by an exact scan.
+ * Other shapes (k up to 512, any E): exact fp32 scores by a SIMT GEMM over chunks of rows + one selection CTA per row.
+ * Either way indices / scores are those of an fp32 evaluation (ties between equal scores: lower index first).
+ * out_idx int64 [B, k], out_scores fp32 [B, k]; 1 <= k <= min(N, 512) (larger k: PBG_ERR_UNSUPPORTED).  Stream-ordered. */
 int pbg_topk_prepare(pbg_ctx* ctx, const float* table, int64_t N, void* stream);
 int pbg_topk(pbg_ctx* ctx, const float* queries, int64_t B, int k, int64_t* out_idx, float* out_scores, void* stream);
+/* Diagnostics: how many query rows of the last pbg_topk chunk (<= 16384 rows) the tensor-core filter could not prove
+ * and handed to the exact scan (0 when the general path ran).  Synchronises `stream`; -1 on error. */
+int64_t pbg_topk_last_flagged(pbg_ctx* ctx, void* stream);
 
 /* Host-side ingest of the CLI's index arrays; replaces json.loads (pro_b_gan_infer.py:485 --input_pairs, :493
  * --input_triplets, :501 --input_entities) + torch.tensor(list) (:135-136, :182, :226).  `text[0..len)` is the JSON

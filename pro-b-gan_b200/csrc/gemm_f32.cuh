@@ -11,7 +11,7 @@
 
 namespace pbg {
 
-enum : int { ACT_LEAKY = 0, ACT_TANH = 1 };
+enum : int { ACT_LEAKY = 0, ACT_TANH = 1, ACT_NONE = 2 };   // ACT_NONE: the plain product, no bias (top-k general path)
 
 struct F32GemmParams {
   const float* A; long long lda;
@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const F32GemmParams p) {
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
       if (n >= p.N) continue;
-      float v = acc[i][j] + p.bias[n];
-      v = (ACT == ACT_LEAKY) ? (v > 0.f ? v : v * p.slope) : tanhf(v);
+      float v = acc[i][j];
+      if (ACT != ACT_NONE) {
+        v += p.bias[n];
+        v = (ACT == ACT_LEAKY) ? (v > 0.f ? v : v * p.slope) : tanhf(v);
+      }
       p.out[m * p.ldo + n] = v;
     }
   }

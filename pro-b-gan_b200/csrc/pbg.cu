@@ -74,7 +74,11 @@ struct TopkState {
   const float* table = nullptr; long long N = 0, n_pad = 0;
   __nv_bfloat16* tn = nullptr; float* inv_t = nullptr; CUtensorMap tm_t;
   long long q_cap = 0; __nv_bfloat16* qn = nullptr; float* inv_q = nullptr; CUtensorMap tm_q;
-  size_t cand_cap = 0; float* cand_score = nullptr; int* cand_idx = nullptr; float* cand_tau = nullptr; int* flag = nullptr;
+  size_t cand_cap = 0; unsigned* cand_grp = nullptr; unsigned* cand_mask = nullptr; int* cand_cnt = nullptr;   // [rows][lists][kTkCand]
+  size_t samp_cap = 0; int* samp_keys = nullptr;   // [rows][sample lists][kTkKeys]
+  float* tau = nullptr; int* flag = nullptr;       // [q_cap]
+  long long last_rows = 0; bool last_filtered = false;   // the last chunk pbg_topk ran (pbg_topk_last_flagged)
+  size_t score_cap = 0; float* score_buf = nullptr;  // general path: exact scores of a chunk of rows [rows, N]
 };
 
 // One staged request (pbg_stage_triplets): the first-layer operands of the pass, gathered + concatenated + cast by the
@@ -662,6 +666,46 @@ int pbg_topk_prepare(pbg_ctx* c, const float* table, int64_t N, void* stream) {
   return PBG_OK;
 }
 
+// Largest k the general path serves: the selection kernel keeps k (score, index) pairs per thread in shared memory.
+constexpr int kTkGeneralMaxK = 512;
+
+namespace {
+// General path (k > kTkMaxK, E != 128, small tables): exact fp32 scores of a chunk of rows through the SIMT GEMM of the
+// parity mode (raw dot products; the row norms are applied by the selection kernel), then one selection CTA per row.
+int topk_general(pbg_ctx* c, TopkState& t, const float* q, long long rows, int k, long long* oi, float* os, cudaStream_t s) {
+  const int E = c->dims.embed_dim;
+  const long long chunk = std::max<long long>(64, std::min<long long>(rows, (512ll << 20) / (4 * t.N)));
+  const size_t need = static_cast<size_t>(chunk) * t.N;
+  if (t.score_cap < need) {
+    PBG_TRY(refuse_growth_in_capture(c, s, "the top-k score buffer"));
+    PBG_CUDA(c, cudaDeviceSynchronize());
+    cudaFree(t.score_buf); t.score_buf = nullptr; t.score_cap = 0;
+    PBG_CUDA(c, cudaMalloc(&t.score_buf, sizeof(float) * need));
+    t.score_cap = need;
+  }
+  const int threads = std::max(32, std::min(256, (200 * 1024 / (k * 8)) / 32 * 32));
+  const size_t smem = static_cast<size_t>(E) * 4 + static_cast<size_t>(threads) * k * 8;
+  static int attr_dev = -1;
+  if (attr_dev != c->dims.device) {
+    PBG_CUDA(c, cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_dev = c->dims.device;
+  }
+  for (long long off = 0; off < rows; off += chunk) {
+    const long long r = std::min(chunk, rows - off);
+    F32GemmParams gp{q + off * E, E, t.table, E, nullptr, t.score_buf, t.N, (int)r, (int)t.N, E, 0.f};
+    dim3 grid((unsigned)((t.N + 63) / 64), (unsigned)((r + 63) / 64));
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      gemm_f32_kernel<ACT_NONE><<<grid, 256, 0, s>>>(gp); }
+    PBG_CUDA(c, cudaGetLastError());
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_exact_kernel<<<static_cast<unsigned>(r), threads, smem, s>>>(q + off * E, t.inv_q + off, t.table, t.inv_t, t.N, E, k,
+                                                                        nullptr, 1, t.score_buf, oi + off * k, os + off * k); }
+    PBG_CUDA(c, cudaGetLastError());
+  }
+  return PBG_OK;
+}
+}  // namespace
+
 int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_idx, float* out_scores, void* stream) {
   if (!c) return PBG_ERR_INVALID;
   TopkState& t = c->tk;
@@ -669,23 +713,27 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
   if (B == 0) return PBG_OK;
   if (!t.table) return fail(c, PBG_ERR_NOT_LOADED, "topk: no table prepared (pbg_topk_prepare)");
   if (!queries || !out_idx || !out_scores) return fail(c, PBG_ERR_INVALID, "null tensor");
-  if (k < 1 || k > 64) return fail(c, PBG_ERR_UNSUPPORTED, "topk: k must be in [1, 64]");
+  if (k < 1) return fail(c, PBG_ERR_INVALID, "topk: k must be positive");
   if (k > t.N) return fail(c, PBG_ERR_INVALID, "topk: k = %d exceeds the %lld rows of the table", k, t.N);  // torch raises too
+  if (k > kTkGeneralMaxK) return fail(c, PBG_ERR_UNSUPPORTED, "topk: k = %d is above the %d this library selects on the device", k, kTkGeneralMaxK);
   PBG_CUDA(c, cudaSetDevice(c->dims.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int E = c->dims.embed_dim;
   const long long kChunk = 16384;
-  const bool filter = E == 128 && k <= kTkMaxK && t.N >= 16 * 256;   // small tables: the exact scan is cheap
+  const bool filter = E == 128 && k <= kTkMaxK && t.N >= 16 * 256;   // small tables / other shapes: the general path
   for (long long off = 0; off < B; off += kChunk) {
     const long long rows = std::min(kChunk, B - off);
     const long long rows_pad = (rows + 255) / 256 * 256;
     const float* q = queries + off * E;
     if (t.q_cap < rows_pad) {
+      PBG_TRY(refuse_growth_in_capture(c, s, "the top-k query buffers"));
       PBG_CUDA(c, cudaDeviceSynchronize());
-      cudaFree(t.qn); cudaFree(t.inv_q); cudaFree(t.flag); t.qn = nullptr; t.inv_q = nullptr; t.flag = nullptr; t.q_cap = 0;
+      cudaFree(t.qn); cudaFree(t.inv_q); cudaFree(t.flag); cudaFree(t.tau);
+      t.qn = nullptr; t.inv_q = nullptr; t.flag = nullptr; t.tau = nullptr; t.q_cap = 0;
       PBG_CUDA(c, cudaMalloc(&t.qn, sizeof(__nv_bfloat16) * rows_pad * E));
       PBG_CUDA(c, cudaMalloc(&t.inv_q, sizeof(float) * rows_pad));
       PBG_CUDA(c, cudaMalloc(&t.flag, sizeof(int) * rows_pad));
+      PBG_CUDA(c, cudaMalloc(&t.tau, sizeof(float) * rows_pad));
       t.q_cap = rows_pad;
       if (E == 128) PBG_TRY(make_tmap(c, &t.tm_q, t.qn, rows_pad, E, 128));
     }
@@ -694,59 +742,86 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
     PBG_CUDA(c, cudaGetLastError());
     long long* oi = reinterpret_cast<long long*>(out_idx) + off * k;
     float* os = out_scores + off * k;
-    if (filter) {
-      const int grid = pass_grid(c) & ~1;
-      const int npairs = grid / 2;
-      TopkParams p;
-      memset(&p, 0, sizeof p);
-      p.tm_q = t.tm_q; p.tm_t = t.tm_t;
-      p.n_rb = static_cast<int>(rows_pad / 256);
-      p.n_tiles = static_cast<int>(t.n_pad / 256);
-      p.n_ranges = std::max(1, std::min({kTkMaxRanges, npairs / p.n_rb, p.n_tiles / kTkSample}));   // items <= pairs: one round
-      p.tiles_per_range = (p.n_tiles + p.n_ranges - 1) / p.n_ranges;
-      p.n_ranges = (p.n_tiles + p.tiles_per_range - 1) / p.tiles_per_range;   // no empty range
-      p.n_items = p.n_rb * p.n_ranges;
-      p.N = t.N;
-      const int n_lists = p.n_ranges * 2;
-      const size_t need = static_cast<size_t>(rows_pad) * n_lists * kTkCand;
-      if (t.cand_cap < need) {
-        PBG_CUDA(c, cudaDeviceSynchronize());
-        cudaFree(t.cand_score); cudaFree(t.cand_idx); cudaFree(t.cand_tau);
-        t.cand_score = nullptr; t.cand_idx = nullptr; t.cand_tau = nullptr; t.cand_cap = 0;
-        PBG_CUDA(c, cudaMalloc(&t.cand_score, sizeof(float) * need));
-        PBG_CUDA(c, cudaMalloc(&t.cand_idx, sizeof(int) * need));
-        PBG_CUDA(c, cudaMalloc(&t.cand_tau, sizeof(float) * need / kTkCand));
-        t.cand_cap = need;
-      }
-      p.cand_score = t.cand_score; p.cand_idx = t.cand_idx; p.cand_tau = t.cand_tau;
-      static int attr_dev = -1;
-      if (attr_dev != c->dims.device) {
-        PBG_CUDA(c, cudaFuncSetAttribute(pbg_topk_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TkSmem::kTotal));
-        PBG_CUDA(c, cudaFuncSetAttribute(topk_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 128 * 4 + 8 * 2 * kTkMaxRanges * kTkCand * 8));
-        attr_dev = c->dims.device;
-      }
-      { LaunchScope ls(c, PBG_K_TOPK, s);
-        pbg_topk_filter_kernel<<<std::min(grid, 2 * p.n_items), kPassThreads, TkSmem::kTotal, s>>>(p); }
-      PBG_CUDA(c, cudaGetLastError());
-      { LaunchScope ls(c, PBG_K_OTHER, s);
-        topk_rescore_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 8 * 128 * 4 + 8 * n_lists * kTkCand * 8, s>>>(
-            q, t.inv_q, t.table, t.inv_t, t.cand_score, t.cand_idx, t.cand_tau, n_lists, rows, k, oi, os, t.flag); }
-      PBG_CUDA(c, cudaGetLastError());
+    t.last_rows = rows; t.last_filtered = filter;
+    if (!filter) {
+      PBG_TRY(topk_general(c, t, q, rows, k, oi, os, s));
+      continue;
     }
-    {
-      static int attr_dev2 = -1;
-      if (attr_dev2 != c->dims.device) {
-        PBG_CUDA(c, cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 4 + 256 * 64 * 8));
-        attr_dev2 = c->dims.device;
-      }
-      // rows the filter could not prove (or every row when the filter does not apply): exact scan, one CTA per row
+    const int grid = pass_grid(c) & ~1;
+    const int npairs = grid / 2;
+    const int n_rb = static_cast<int>(rows_pad / 256);
+    const int n_tiles = static_cast<int>(t.n_pad / 256);
+    // work items = query block x tile range, about one round over the pairs
+    auto split = [&](int tiles, TopkParams& p) {
+      p.n_rb = n_rb;
+      p.n_tiles = tiles;
+      p.n_ranges = std::max(1, std::min({kTkMaxRanges, npairs / n_rb, tiles}));
+      p.tiles_per_range = (tiles + p.n_ranges - 1) / p.n_ranges;
+      p.n_ranges = (tiles + p.tiles_per_range - 1) / p.tiles_per_range;   // no empty range
+      p.n_items = n_rb * p.n_ranges;
+    };
+    TopkParams ps, pm;
+    memset(&ps, 0, sizeof ps); memset(&pm, 0, sizeof pm);
+    ps.tm_q = pm.tm_q = t.tm_q; ps.tm_t = pm.tm_t = t.tm_t; ps.N = pm.N = t.N;
+    ps.tile_stride = kTkSampleStride; pm.tile_stride = 1;
+    split((n_tiles + kTkSampleStride - 1) / kTkSampleStride, ps);
+    split(n_tiles, pm);
+    const int n_slists = ps.n_ranges * 2, n_lists = pm.n_ranges * 2;
+    const size_t need = static_cast<size_t>(rows_pad) * n_lists * kTkCand;
+    const size_t sneed = static_cast<size_t>(rows_pad) * n_slists * kTkKeys;
+    if (t.cand_cap < need || t.samp_cap < sneed) {
+      PBG_TRY(refuse_growth_in_capture(c, s, "the top-k candidate buffers"));
+      PBG_CUDA(c, cudaDeviceSynchronize());
+      cudaFree(t.cand_grp); cudaFree(t.cand_mask); cudaFree(t.cand_cnt); cudaFree(t.samp_keys);
+      t.cand_grp = t.cand_mask = nullptr; t.cand_cnt = nullptr; t.samp_keys = nullptr; t.cand_cap = t.samp_cap = 0;
+      PBG_CUDA(c, cudaMalloc(&t.cand_grp, sizeof(unsigned) * need));
+      PBG_CUDA(c, cudaMalloc(&t.cand_mask, sizeof(unsigned) * need));
+      PBG_CUDA(c, cudaMalloc(&t.cand_cnt, sizeof(int) * need / kTkCand));
+      PBG_CUDA(c, cudaMalloc(&t.samp_keys, sizeof(int) * sneed));
+      t.cand_cap = need; t.samp_cap = sneed;
+    }
+    ps.samp_keys = t.samp_keys;
+    pm.tau = t.tau; pm.cand_grp = t.cand_grp; pm.cand_mask = t.cand_mask; pm.cand_cnt = t.cand_cnt;
+    static int attr_dev = -1;
+    if (attr_dev != c->dims.device) {
+      PBG_CUDA(c, cudaFuncSetAttribute(pbg_topk_scan_kernel<TK_SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TkSmem::kTotal));
+      PBG_CUDA(c, cudaFuncSetAttribute(pbg_topk_scan_kernel<TK_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TkSmem::kTotal));
+      PBG_CUDA(c, cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_dev = c->dims.device;
+    }
+    { LaunchScope ls(c, PBG_K_TOPK, s);
+      pbg_topk_scan_kernel<TK_SAMPLE><<<std::min(grid, 2 * ps.n_items), kPassThreads, TkSmem::kTotal, s>>>(ps); }
+    PBG_CUDA(c, cudaGetLastError());
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_tau_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(t.samp_keys, n_slists, rows, rows_pad, k, t.tau); }
+    PBG_CUDA(c, cudaGetLastError());
+    { LaunchScope ls(c, PBG_K_TOPK, s);
+      pbg_topk_scan_kernel<TK_SCAN><<<std::min(grid, 2 * pm.n_items), kPassThreads, TkSmem::kTotal, s>>>(pm); }
+    PBG_CUDA(c, cudaGetLastError());
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_rescore_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask,
+                                                                                t.cand_cnt, t.tau, n_lists, rows, t.N, k, oi, os, t.flag); }
+    PBG_CUDA(c, cudaGetLastError());
+    { // rows the filter could not prove: exact scan, one CTA per row (rare)
       LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_exact_kernel<<<static_cast<unsigned>(rows), 256, E * 4 + 256 * k * 8, s>>>(q, t.inv_q, t.table, t.inv_t, t.N, E, k, t.flag,
-                                                                                     filter ? 0 : 1, oi, os);
-    }
+      topk_exact_kernel<<<static_cast<unsigned>(rows), 256, E * 4 + 256 * k * 8, s>>>(q, t.inv_q, t.table, t.inv_t, t.N, E, k, t.flag, 0,
+                                                                                     nullptr, oi, os); }
     PBG_CUDA(c, cudaGetLastError());
   }
   return PBG_OK;
+}
+
+int64_t pbg_topk_last_flagged(pbg_ctx* c, void* stream) {
+  if (!c) return -1;
+  TopkState& t = c->tk;
+  if (!t.last_filtered || t.last_rows <= 0) return 0;
+  if (cudaSetDevice(c->dims.device) != cudaSuccess) return -1;
+  std::vector<int> h(static_cast<size_t>(t.last_rows));
+  if (cudaMemcpyAsync(h.data(), t.flag, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  int64_t n = 0;
+  for (int v : h) n += v != 0;
+  return n;
 }
 
 int pbg_set_result_mirrors(pbg_ctx* c, int n, void* const* gen_out, float* const* gen_scores, float* const* logits,
@@ -839,7 +914,8 @@ void pbg_destroy(pbg_ctx* c) {
   free_stage(c->stage[0]); free_stage(c->stage[1]);
   cudaFree(c->err_flag); cudaFree(c->trace);
   cudaFree(c->tk.tn); cudaFree(c->tk.inv_t); cudaFree(c->tk.qn); cudaFree(c->tk.inv_q);
-  cudaFree(c->tk.cand_score); cudaFree(c->tk.cand_idx); cudaFree(c->tk.cand_tau); cudaFree(c->tk.flag);
+  cudaFree(c->tk.cand_grp); cudaFree(c->tk.cand_mask); cudaFree(c->tk.cand_cnt); cudaFree(c->tk.flag);
+  cudaFree(c->tk.samp_keys); cudaFree(c->tk.tau); cudaFree(c->tk.score_buf);
 
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
   cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);

@@ -4,20 +4,25 @@
 //   similarities = pred_norm @ entity_norm.T;  top_scores, top_indices = similarities.topk(k, dim=1)
 //                                               (pro_b_gan_infer.py:146-151, :231-236)
 //
-// The [B, N] similarity matrix (1 GiB at B = 4096, N = 65536) never exists.  Three steps:
-//   1. prepare   : row norms; bf16 copies of the normalised table / queries, zero padded to 256 rows   (HBM-bound)
-//   2. filter    : bf16 tensor-core scores, CTA pairs (tcgen05.mma.cta_group::2, M = 256 queries x N = 256 entities
-//                  per MMA group, K = E = 128), the query tile stationary in shared memory, entity tiles streamed by
-//                  TMA; the matrix goes TMEM -> registers -> compare only.  Per query row and per (entity range,
-//                  column half) the epilogue first tracks the 6 best scores of a sample (the range's first 16 tiles)
-//                  in registers, branch-free, as packed (score | position) integer keys; the 6th becomes the list's
-//                  cut-off and every later score above it is appended to a thread-private shared-memory list
-//                  (about 19 entries; a warp vote keeps the common case at three instructions per score)
-//   3. rescore   : exact fp32 cosine of every candidate, top-k among them (ties: lower index first), and a proof
-//                  obligation per row: the k-th exact score must beat every list's cut-off by more than the bf16 error
-//                  bound, else the row is flagged and re-done by an exact scan of the table (rare; always used for
-//                  k > 16 or E != 128)
+// The [B, N] similarity matrix (1 GiB at B = 4096, N = 65536) never exists.  Steps (E = 128, k <= 16):
+//   1. prepare : row norms; bf16 copies of the normalised table / queries, zero padded to 256 rows        (HBM-bound)
+//   2. sample  : bf16 tensor-core scores (CTA pairs, tcgen05.mma.cta_group::2, M = 256 queries x N = 256 entities per
+//                MMA group, K = E = 128; query tile stationary, entity tiles streamed by TMA) of every 8th entity
+//                tile.  Epilogue per query row (one thread each): the maximum of every 32 scores as a packed
+//                (score | position) integer key -- one LOP3 per score and a three-input max tree -- pushed through a
+//                16-deep sorted insert once per 32 scores.  A small kernel merges a row's lists: tau[row] = the k-th
+//                best sampled score, i.e. at least k entities score >= tau.
+//   3. scan    : the same MMA pipeline over ALL entity tiles; the matrix goes TMEM -> registers -> compare only.  Per
+//                score: one compare with tau and one bit into a 32-bit mask -- no vote, no branch per score; per 32
+//                scores a mask that is not empty is appended with its group number to a thread-private list in global memory
+//                (about k * 8 / lists entries per list).
+//   4. rescore : exact fp32 cosine of every entity whose bit is set, top-k among them (ties: lower index first), and
+//                a proof obligation per row: the k-th exact score must beat tau by more than the bf16 error bound --
+//                everything that was not a candidate has a bf16 score <= tau -- else the row is flagged and re-done
+//                by an exact scan of the table (rare).
 // so the returned indices are those of an exact fp32 evaluation, not of the bf16 scores.
+// Other shapes (k > 16, E != 128, small tables): exact fp32 scores of a chunk of rows by the SIMT GEMM of the parity
+// mode, then one selection CTA per row (pbg.cu: topk_general).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -27,33 +32,37 @@
 namespace pbg {
 
 constexpr int kTkStages = 4;          // entity tiles in flight per CTA (32 KB each: 128 entities x 128 dims bf16)
-constexpr int kTkCand = 32;           // candidates kept per (row, entity range, column half)
+constexpr int kTkCand = 160;          // (group, mask) entries kept per (row, entity range, column half), in global memory
 constexpr int kTkMaxRanges = 16;
-constexpr int kTkMaxK = 16;           // largest k the filter path proves exact; above it the exact scan runs
-constexpr int kTkSample = 16;         // tiles of a range whose 6 best scores set the list's cut-off
+constexpr int kTkMaxK = 16;           // largest k of the filter path; above it the general path runs
+constexpr int kTkSampleStride = 8;    // every 8th 256-entity tile is sampled for the cut-off
+constexpr int kTkKeys = 16;           // best group keys a thread keeps per sample list (>= kTkMaxK)
+constexpr int kTkRescoreMax = 512;    // candidates per row the rescoring kernel takes; more: exact scan
 constexpr float kTkErrBound = 0.009f; // |bf16 score - exact score| <= 2^-8 (unit vectors, 8-bit mantissas) + key truncation + slack
+enum : int { TK_SAMPLE = 0, TK_SCAN = 1 };
 
 struct alignas(64) TopkParams {
   CUtensorMap tm_q;      // normalised queries bf16 [Bpad, 128]: box 64 x 128 rows
   CUtensorMap tm_t;      // normalised table   bf16 [Npad, 128]: box 64 x 128 rows (one CTA's half of a 256-entity tile)
   int n_rb;              // 256-row query blocks
-  int n_ranges;          // entity ranges (work item = query block x range)
-  int tiles_per_range;   // 256-entity tiles per range
-  int n_tiles;           // Npad / 256
+  int n_ranges;          // tile ranges (work item = query block x range)
+  int tiles_per_range;   // visited tiles per range
+  int n_tiles;           // visited tiles: every tile (scan) or every kTkSampleStride-th (sample)
+  int tile_stride;       // table tile = visited tile * tile_stride
   int n_items;           // n_rb * n_ranges
   long long N;           // valid entities
-  float* cand_score;     // [Bpad][n_ranges * 2][kTkCand]
-  int* cand_idx;
-  float* cand_tau;       // [Bpad][n_ranges * 2]: the list's cut-off (its smallest kept approximate score)
+  int* samp_keys;        // sample: [Bpad][n_ranges * 2][kTkKeys] best group keys, descending
+  const float* tau;      // scan:   [Bpad] cut-off per query row
+  unsigned* cand_grp;    // scan:   [Bpad][n_ranges * 2][kTkCand] 32-entity group numbers ...
+  unsigned* cand_mask;   //         ... and which of the group's entities scored above tau
+  int* cand_cnt;         // scan:   [Bpad][n_ranges * 2] groups found (more than kTkCand: the list overflowed)
 };
 
 struct TkSmem {
   static constexpr int kQ = 2 * 128 * kBlockK * 2;        // this CTA's 128 query rows, 2 k-blocks
   static constexpr int kT = 2 * 128 * kBlockK * 2;        // this CTA's 128 entities of a tile, 2 k-blocks
   static constexpr int kStageOff = kQ;
-  static constexpr int kListOff = kStageOff + kTkStages * kT;
-  static constexpr int kListPerWarp = kTkCand * 32 * 8;   // [entry][lane] scores, then indices
-  static constexpr int kBarOff = kListOff + kEpiWarps * kListPerWarp;
+  static constexpr int kBarOff = kStageOff + kTkStages * kT;
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 static_assert(TkSmem::kTotal <= 232448, "topk: shared memory budget");
@@ -87,50 +96,19 @@ __global__ void __launch_bounds__(256) topk_prepare_kernel(const float* __restri
   }
 }
 
-// ------------------------------------------------------------------------------------------------ 2. filter
-// Thread-private candidate list in shared memory, laid out [entry][lane] so that a warp's accesses never conflict.
-// Insert: replace the smallest kept score, return the new cut-off.  Out of line: it runs a few hundred times per list,
-// the compare in front of it 8192 times per tile.
-__device__ __noinline__ float tk_insert(float* sc, int* ix, int lane, float s, int idx) {
-  int at = 0; float mn = sc[lane];
-#pragma unroll
-  for (int e = 1; e < kTkCand; ++e) { const float v = sc[e * 32 + lane]; if (v < mn) { mn = v; at = e; } }
-  sc[at * 32 + lane] = s; ix[at * 32 + lane] = idx;
-  mn = sc[lane];
-#pragma unroll
-  for (int e = 1; e < kTkCand; ++e) mn = fminf(mn, sc[e * 32 + lane]);
-  return mn;
+// ------------------------------------------------------------------------------------------------ 2 / 3. sample, scan
+// MODE TK_SAMPLE: visited tiles are every kTkSampleStride-th tile; per (row, range, column half) the kTkKeys best group
+//                 keys go to samp_keys.  MODE TK_SCAN: every tile; (group, mask) candidate lists.
+// (score bits with the low 5 bits replaced by the position) as ONE lop3: (a & b) | c
+__device__ __forceinline__ int tk_key(uint32_t bits, int j) {
+  int d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(bits), "r"(0xFFFFFFE0u), "r"(j));
+  return d;
 }
 
-// A warp reaches this when some lane's score beat its cut-off: the passing lanes append to their lists (or, list
-// full, replace its smallest and raise the cut-off).  Returns (entries << 32) | cut-off bits.  Out of line: about one
-// score in eight gets here, and the inlined alternative is 128 copies of this body per tile.
-__device__ __noinline__ unsigned long long tk_pass(float* sc, int* ix, int lane, bool pass, float sv, int idx, int cnt, float tau) {
-  if (pass) {
-    if (cnt < kTkCand) {
-      sc[cnt * 32 + lane] = sv; ix[cnt * 32 + lane] = idx; ++cnt;
-      if (cnt == kTkCand) {
-        float mn = sc[lane];
-#pragma unroll
-        for (int e = 1; e < kTkCand; ++e) mn = fminf(mn, sc[e * 32 + lane]);
-        tau = fmaxf(tau, mn);
-      }
-    } else {
-      tau = tk_insert(sc, ix, lane, sv, idx);
-    }
-  }
-  return (static_cast<unsigned long long>(static_cast<unsigned>(cnt)) << 32) | __float_as_uint(tau);
-}
-
-__device__ __noinline__ float tk_list_min(const float* sc, int lane) {
-  float mn = sc[lane];
-#pragma unroll
-  for (int e = 1; e < kTkCand; ++e) mn = fminf(mn, sc[e * 32 + lane]);
-  return mn;
-}
-
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPassThreads, 1)
-pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
+pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
   using L = TkSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -186,7 +164,8 @@ pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * L::kT);
           uint8_t* st = smem + L::kStageOff + stage * L::kT;
           for (int kb = 0; kb < 2; ++kb)
-            tma_load_2d_pair(st + kb * (L::kT / 2), &p.tm_t, lead_full + stage * 8, kb * kBlockK, t * 256 + static_cast<int>(rank) * 128);
+            tma_load_2d_pair(st + kb * (L::kT / 2), &p.tm_t, lead_full + stage * 8, kb * kBlockK,
+                             t * p.tile_stride * 256 + static_cast<int>(rank) * 128);
           if (++stage == kTkStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,61 +205,55 @@ pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ filter warps (both CTAs)
+    // ------------------------------------------------------------ filter warps (both CTAs): one query row per thread
     const int wep = warp - 2, q = warp & 3, half = wep >> 2;
-    float* lsc = reinterpret_cast<float*>(smem + L::kListOff + wep * L::kListPerWarp);
-    int* lix = reinterpret_cast<int*>(lsc + kTkCand * 32);
     uint32_t acc = 0, acc_phase = 0;
     for (int item = pair; item < p.n_items; item += npairs) {
       const int rb = item / p.n_ranges, rg = item % p.n_ranges;
-#pragma unroll
-      for (int e = 0; e < kTkCand; ++e) { lsc[e * 32 + lane] = -3.0e38f; lix[e * 32 + lane] = -1; }
+      const long long row = static_cast<long long>(rb) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
       const int t0 = rg * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
-      const int ts_end = min(t1, t0 + kTkSample);
-      int m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0, m6 = 0;   // sample phase: the 6 largest keys, sorted
-      float tau = 0.f;                                       // main phase: cut-off
-      int cnt = 0;                                           // entries in the list
+      int m[kTkKeys];                       // sample: the best group keys so far, descending
+#pragma unroll
+      for (int i = 0; i < kTkKeys; ++i) m[i] = 0;
+      const float tau = MODE == TK_SCAN ? p.tau[row] : 0.f;
+      const long long lbase = row * (p.n_ranges * 2) + rg * 2 + half;
+      // scan: the list lives in global memory -- an append is one predicated 8-byte pair of stores every few thousand
+      // scores per thread, and its length is then bounded by memory, not by what is left of shared memory
+      unsigned* lgrp = MODE == TK_SCAN ? p.cand_grp + lbase * kTkCand : nullptr;
+      unsigned* lmsk = MODE == TK_SCAN ? p.cand_mask + lbase * kTkCand : nullptr;
+      int cnt = 0;                          // scan: groups appended (may run past kTkCand: overflow)
       for (int t = t0; t < t1; ++t) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + half * 128;
-        const int ent0 = t * 256 + half * 128;
-        const bool sampling = t < ts_end;
-        const int tsb = (t - t0) << 7;
+        const unsigned grp0 = static_cast<unsigned>(t * p.tile_stride) * 8u + static_cast<unsigned>(half) * 4u;   // 32-entity groups
         uint32_t va[32], vb[32];
-        // one 32-column group: sample phase -> packed (score | position) keys through a 6-deep compare-exchange chain;
-        // main phase -> compare with the cut-off, a warp vote, the rare append out of line
         auto process = [&](const uint32_t (&cur)[32], int g) {
-          if (sampling) {
-            // non-negative floats order like integers; negatives clamp to 0; the low 12 bits carry the position
-            const int pb = tsb | (g << 5);
+          if (MODE == TK_SAMPLE) {
+            // positive floats order like integers and negative ones are negative integers: a signed max with a floor
+            // of 0 is the float max of the positives; the low 5 bits carry the position (a tie-break, never decoded)
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int k = (max(static_cast<int>(cur[j]), 0) & ~0xFFF) | (pb | j);
-              // sorted insert, every level from the OLD values (depth 2 instead of a 11-deep dependent chain):
-              // new m_i = max(m_i, min(m_{i-1}, k))
-              const int n6 = max(m6, min(m5, k)), n5 = max(m5, min(m4, k)), n4 = max(m4, min(m3, k));
-              const int n3 = max(m3, min(m2, k)), n2 = max(m2, min(m1, k)), n1 = max(m1, k);
-              m1 = n1; m2 = n2; m3 = n3; m4 = n4; m5 = n5; m6 = n6;
+            for (int j = 0; j < 32; j += 8) {
+              a0 = __vimax3_s32(a0, tk_key(cur[j + 0], j + 0), tk_key(cur[j + 1], j + 1));
+              a1 = __vimax3_s32(a1, tk_key(cur[j + 2], j + 2), tk_key(cur[j + 3], j + 3));
+              a2 = __vimax3_s32(a2, tk_key(cur[j + 4], j + 4), tk_key(cur[j + 5], j + 5));
+              a3 = __vimax3_s32(a3, tk_key(cur[j + 6], j + 6), tk_key(cur[j + 7], j + 7));
             }
+            const int a = max(__vimax3_s32(a0, a1, a2), a3);
+            // sorted insert, every level from the old value above it: m_i = max(m_i, min(m_{i-1}, a))
+#pragma unroll
+            for (int i = kTkKeys - 1; i > 0; --i) m[i] = max(m[i], min(m[i - 1], a));
+            m[0] = max(m[0], a);
           } else {
-            // four scores per warp vote: the control flow around a vote costs more than the compares
-            const int e0 = ent0 + g * 32;
+            // two instructions per score: tau - s is negative exactly when s > tau (tau >= 0), and a funnel shift moves
+            // that sign bit into the mask; score j ends up at bit 31 - j
+            unsigned mask = 0u;
 #pragma unroll
-            for (int j4 = 0; j4 < 32; j4 += 4) {
-              const float s0 = __uint_as_float(cur[j4]), s1 = __uint_as_float(cur[j4 + 1]);
-              const float s2 = __uint_as_float(cur[j4 + 2]), s3 = __uint_as_float(cur[j4 + 3]);
-              if (__any_sync(0xffffffffu, fmaxf(fmaxf(s0, s1), fmaxf(s2, s3)) > tau)) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float sv = __uint_as_float(cur[j4 + u]);
-                  const bool pass = sv > tau;
-                  if (__any_sync(0xffffffffu, pass)) {
-                    const unsigned long long r = tk_pass(lsc, lix, lane, pass && e0 + j4 + u < p.N, sv, e0 + j4 + u, cnt, tau);
-                    cnt = static_cast<int>(r >> 32); tau = __uint_as_float(static_cast<unsigned>(r));
-                  }
-                }
-              }
+            for (int j = 0; j < 32; ++j) mask = __funnelshift_l(__float_as_uint(tau - __uint_as_float(cur[j])), mask, 1);
+            if (mask != 0u) {
+              if (cnt < kTkCand) { lgrp[cnt] = grp0 + static_cast<unsigned>(g); lmsk[cnt] = mask; }
+              ++cnt;
             }
           }
         };
@@ -300,28 +273,14 @@ pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
           }
           process(vb, 2 * gp + 1);
         }
-        if (t + 1 == ts_end) {
-          // end of the sample: the 6 winners open the list, the 6th (truncated) score is the cut-off
-          const int ms[6] = {m1, m2, m3, m4, m5, m6};
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int pos = ms[i] & 0xFFF;
-            const int ent = (t0 + (pos >> 7)) * 256 + half * 128 + (pos & 127);
-            if ((ms[i] >> 12) != 0 && ent < p.N) { lsc[cnt * 32 + lane] = __int_as_float(ms[i] & ~0xFFF); lix[cnt * 32 + lane] = ent; ++cnt; }
-          }
-          tau = __int_as_float(m6 & ~0xFFF);
-        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      // hand this (row, range, half) list to the rescoring kernel
-      const long long row = static_cast<long long>(rb) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
-      const long long lbase = (row * (p.n_ranges * 2) + rg * 2 + half);
-#pragma unroll 4
-      for (int e = 0; e < kTkCand; ++e) {
-        p.cand_score[lbase * kTkCand + e] = lsc[e * 32 + lane];
-        p.cand_idx[lbase * kTkCand + e] = lix[e * 32 + lane];
+      if (MODE == TK_SAMPLE) {
+#pragma unroll
+        for (int i = 0; i < kTkKeys; ++i) p.samp_keys[lbase * kTkKeys + i] = m[i];
+      } else {
+        p.cand_cnt[lbase] = cnt;
       }
-      p.cand_tau[lbase] = tau;
     }
   }
   tc_fence_before();
@@ -333,23 +292,56 @@ pbg_topk_filter_kernel(const __grid_constant__ TopkParams p) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------ 3. rescore
-// One warp per query row (E = 128): exact scores of the candidates, the k best (descending; ties: lower index), and the
-// proof that nothing outside the candidate lists can belong to them.  flag[row] = 1 asks for the exact scan.
-// Each lane scores one candidate at a time (its whole 128-dim dot, the normalised query broadcast from shared memory):
-// 32 candidates and 32 independent row reads in flight per warp, no shuffles.
+// One warp per query row: tau = the k-th largest of the row's sampled group keys (n_lists x kTkKeys of them), with its
+// position bits cleared -- at least k sampled entities score >= tau.  Fewer than k positive keys: tau = 0.
+__global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ samp_keys, int n_lists, long long B, long long rows_pad,
+                                                       int k, float* __restrict__ tau) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows_pad) return;
+  if (row >= B) { if (lane == 0) tau[row] = 0.f; return; }
+  const int n = n_lists * kTkKeys;           // <= 32 lists x 16 keys: 16 per lane
+  int mine[kTkKeys];
+#pragma unroll
+  for (int i = 0; i < kTkKeys; ++i) { const int c = i * 32 + lane; mine[i] = c < n ? samp_keys[row * n + c] : 0; }
+  int kth = 0;
+  for (int r = 0; r < k; ++r) {
+    int best = 0, at = 0;
+#pragma unroll
+    for (int i = 0; i < kTkKeys; ++i) if (mine[i] > best) { best = mine[i]; at = i; }
+    int wbest = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wbest = max(wbest, __shfl_xor_sync(0xffffffffu, wbest, o));
+    // remove one instance of the winner (the lowest lane that holds it)
+    const unsigned who = __ballot_sync(0xffffffffu, best == wbest && wbest > 0);
+    if (who != 0u && lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int i = 0; i < kTkKeys; ++i) if (i == at) mine[i] = 0;
+    }
+    kth = wbest;
+  }
+  if (lane == 0) tau[row] = kth > 0 ? __int_as_float(kth & ~0x1F) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ 4. rescore
+// One warp per query row (E = 128): the candidates are the set bits of the row's (group, mask) lists.  Exact scores,
+// the k best (descending; ties: lower index), and the proof that nothing else can belong to them: everything that is
+// not a candidate has a bf16 score <= tau.  flag[row] = 1 asks for the exact scan (list overflow, too many or too few
+// candidates, proof failed).  Each lane scores one candidate at a time (its whole 128-dim dot, the normalised query
+// broadcast from shared memory): 32 candidates and 32 independent row reads in flight per warp, no shuffles.
 __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restrict__ q, const float* __restrict__ inv_q,
                                                            const float* __restrict__ table, const float* __restrict__ inv_t,
-                                                           const float* __restrict__ cand_score, const int* __restrict__ cand_idx,
-                                                           const float* __restrict__ cand_tau, int n_lists, long long B, int k,
+                                                           const unsigned* __restrict__ cand_grp, const unsigned* __restrict__ cand_mask,
+                                                           const int* __restrict__ cand_cnt, const float* __restrict__ tau,
+                                                           int n_lists, long long B, long long N, int k,
                                                            long long* __restrict__ out_idx, float* __restrict__ out_score,
                                                            int* __restrict__ flag) {
-  extern __shared__ uint8_t sm[];
+  __shared__ float qn_s[8][128];
+  __shared__ float es_s[8][kTkRescoreMax];
+  __shared__ int ei_s[8][kTkRescoreMax];
+  __shared__ int cnt_s[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int ncand = n_lists * kTkCand;
-  float* qn = reinterpret_cast<float*>(sm) + w * 128;                                 // [8][128] normalised queries
-  float* es = reinterpret_cast<float*>(sm) + 8 * 128 + static_cast<size_t>(w) * ncand * 2;   // exact scores
-  int* ei = reinterpret_cast<int*>(es + ncand);
+  float* qn = qn_s[w]; float* es = es_s[w]; int* ei = ei_s[w];
   const long long row = static_cast<long long>(blockIdx.x) * 8 + w;
   if (row >= B) return;
   {
@@ -358,28 +350,45 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restri
     v.x *= iq; v.y *= iq; v.z *= iq; v.w *= iq;
     *reinterpret_cast<float4*>(qn + 4 * lane) = v;
   }
-  const long long cb = row * n_lists * kTkCand;
-  float tau_max = -3.0e38f;
-  for (int l = lane; l < n_lists; l += 32) tau_max = fmaxf(tau_max, cand_tau[row * n_lists + l]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tau_max = fmaxf(tau_max, __shfl_xor_sync(0xffffffffu, tau_max, o));
+  if (lane == 0) cnt_s[w] = 0;
   __syncwarp();
-  for (int c = lane; c < ncand; c += 32) {
-    const int idx = cand_idx[cb + c];
-    float s = -3.0e38f;
-    if (idx >= 0) {
-      const float it = inv_t[idx];
-      const float4* tr = reinterpret_cast<const float4*>(table + static_cast<long long>(idx) * 128);
-      float d = 0.f;
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j) {
-        const float4 tv = __ldg(tr + j);
-        const float4 qv = *reinterpret_cast<const float4*>(qn + 4 * j);
-        d += qv.x * (tv.x * it) + qv.y * (tv.y * it) + qv.z * (tv.z * it) + qv.w * (tv.w * it);
+  // decode: lane l walks list l (n_lists <= 32)
+  bool bad = false;
+  if (lane < n_lists) {
+    const long long lb = row * n_lists + lane;
+    const int c = cand_cnt[lb];
+    bad = c > kTkCand;
+    for (int e = 0; e < min(c, kTkCand); ++e) {
+      const unsigned g = cand_grp[lb * kTkCand + e];
+      unsigned mk = cand_mask[lb * kTkCand + e];
+      while (mk != 0u) {
+        const int b = __ffs(mk) - 1;
+        mk &= mk - 1u;
+        const long long ent = static_cast<long long>(g) * 32 + (31 - b);   // the scan shifts score j in at bit 31 - j
+        if (ent < N) {
+          const int pos = atomicAdd(&cnt_s[w], 1);
+          if (pos < kTkRescoreMax) ei[pos] = static_cast<int>(ent);
+        }
       }
-      s = d;
     }
-    es[c] = s; ei[c] = idx;
+  }
+  __syncwarp();
+  const int ncand_all = cnt_s[w];
+  bad = __any_sync(0xffffffffu, bad) || ncand_all > kTkRescoreMax || ncand_all < k;
+  if (bad) { if (lane == 0) flag[row] = 1; return; }
+  const int ncand = ncand_all;
+  for (int c = lane; c < ncand; c += 32) {
+    const int idx = ei[c];
+    const float it = inv_t[idx];
+    const float4* tr = reinterpret_cast<const float4*>(table + static_cast<long long>(idx) * 128);
+    float d = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float4 tv = __ldg(tr + j);
+      const float4 qv = *reinterpret_cast<const float4*>(qn + 4 * j);
+      d += qv.x * (tv.x * it) + qv.y * (tv.y * it) + qv.z * (tv.z * it) + qv.w * (tv.w * it);
+    }
+    es[c] = d;
   }
   __syncwarp();
   float kth = -3.0e38f;
@@ -403,37 +412,49 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restri
     kth = best;
     __syncwarp();
   }
-  // nothing outside the lists can reach the k-th exact score: every such entity's bf16 score is <= its list's cut-off
-  if (lane == 0) flag[row] = (kth > tau_max + kTkErrBound) ? 0 : 1;
+  // nothing outside the candidate set can reach the k-th exact score: its bf16 score is <= tau
+  if (lane == 0) flag[row] = (kth > tau[row] + kTkErrBound) ? 0 : 1;
 }
 
-// Exact scan of the whole table for the rows whose flag is set (or all rows: always == 1): one CTA per row, every thread
-// keeps the k best of its entities, the CTA merges.  Slow by design (fp32 SIMT over N x E) -- the proof above fails rarely.
+// Exact selection, one CTA per row: every thread keeps the k best of its entities, the CTA merges (k rounds of a block
+// arg-max; ties: lower index first).  Two uses: rows whose flag is set after the filter path (always == 0; the scores
+// are computed here, fp32 SIMT over N x E -- slow by design, the proof fails rarely), and the general path
+// (always == 1, raw != nullptr: the row's raw dot products [N] come from the fp32 GEMM, the row norms are applied here).
 __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict__ q, const float* __restrict__ inv_q,
                                                          const float* __restrict__ table, const float* __restrict__ inv_t, long long N,
                                                          int E, int k, const int* __restrict__ flag, int always,
-                                                         long long* __restrict__ out_idx, float* __restrict__ out_score) {
+                                                         const float* __restrict__ raw, long long* __restrict__ out_idx,
+                                                         float* __restrict__ out_score) {
   extern __shared__ uint8_t sm[];
   const long long row = blockIdx.x;
   if (!always && flag[row] == 0) return;
+  const int nt = blockDim.x;
   float* qn = reinterpret_cast<float*>(sm);                 // [E]
-  float* ms = qn + E;                                       // [256 * k] merged candidates
-  int* mi = reinterpret_cast<int*>(ms + 256 * k);
+  float* ms = qn + E;                                       // [nt * k] kept candidates
+  int* mi = reinterpret_cast<int*>(ms + nt * k);
   const float iq = inv_q[row];
-  for (int c = threadIdx.x; c < E; c += blockDim.x) qn[c] = q[row * E + c] * iq;
+  for (int c = threadIdx.x; c < E; c += nt) qn[c] = q[row * E + c] * iq;
   __syncthreads();
   float* mys = ms + threadIdx.x * k; int* myi = mi + threadIdx.x * k;
   for (int j = 0; j < k; ++j) { mys[j] = -3.0e38f; myi[j] = -1; }
   float tau = -3.0e38f;
-  for (long long e = threadIdx.x; e < N; e += blockDim.x) {
+  int filled = 0;
+  for (long long e = threadIdx.x; e < N; e += nt) {
     const float it = inv_t[e];
-    const float* tr = table + e * E;
     float d = 0.f;
-    for (int c = 0; c < E; c += 4) {
-      const float4 tv = *reinterpret_cast<const float4*>(tr + c);
-      d += qn[c] * (tv.x * it) + qn[c + 1] * (tv.y * it) + qn[c + 2] * (tv.z * it) + qn[c + 3] * (tv.w * it);
+    if (raw != nullptr) {
+      d = raw[row * N + e] * iq * it;
+    } else {
+      const float* tr = table + e * E;
+      for (int c = 0; c < E; c += 4) {
+        const float4 tv = *reinterpret_cast<const float4*>(tr + c);
+        d += qn[c] * (tv.x * it) + qn[c + 1] * (tv.y * it) + qn[c + 2] * (tv.z * it) + qn[c + 3] * (tv.w * it);
+      }
     }
-    if (d > tau) {   // replace this thread's smallest
+    if (filled < k) {              // the first k entities of a thread are simply kept
+      mys[filled] = d; myi[filled] = static_cast<int>(e); ++filled;
+      if (filled == k) { float mn = mys[0]; for (int j = 1; j < k; ++j) mn = fminf(mn, mys[j]); tau = mn; }
+    } else if (d > tau) {          // replace this thread's smallest
       int at = 0; float mn = mys[0];
       for (int j = 1; j < k; ++j) if (mys[j] < mn) { mn = mys[j]; at = j; }
       mys[at] = d; myi[at] = static_cast<int>(e);
@@ -443,11 +464,12 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
     }
   }
   __syncthreads();
-  // k rounds of a block-wide arg-max over the 256 * k kept candidates (warp 0 does the final step)
+  // k rounds of a block-wide arg-max over the kept candidates (thread 0 does the final step)
   __shared__ float rs[8]; __shared__ int ri[8], rc[8];
+  const int nw = nt >> 5;
   for (int r = 0; r < k; ++r) {
     float best = -3.0e38f; int bi = 0x7fffffff, bc = -1;
-    for (int c = threadIdx.x; c < 256 * k; c += blockDim.x) {
+    for (int c = threadIdx.x; c < nt * k; c += nt) {
       const float s = ms[c]; const int idx = mi[c];
       if (idx >= 0 && (s > best || (s == best && idx < bi))) { best = s; bi = idx; bc = c; }
     }
@@ -460,7 +482,7 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
     if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = best; ri[threadIdx.x >> 5] = bi; rc[threadIdx.x >> 5] = bc; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int j = 1; j < 8; ++j)
+      for (int j = 1; j < nw; ++j)
         if (rs[j] > best || (rs[j] == best && ri[j] < bi)) { best = rs[j]; bi = ri[j]; bc = rc[j]; }
       out_idx[row * k + r] = bc >= 0 ? bi : -1;
       out_score[row * k + r] = best;

@@ -81,8 +81,7 @@ class Engine:
         The prepared (normalised) table is cached until the tensor is modified or another table is passed."""
         table = self._f32(table, self.E, "table")
         queries = self._f32(queries, self.E, "queries")
-        if k > table.shape[0]:
-            raise RuntimeError(f"selected index k out of range: k = {k} > {table.shape[0]} rows")  # what torch.topk raises
+        self.validate_top_k(k, table.shape[0])
         key = (table.data_ptr(), tuple(table.shape), table._version)
         with torch.cuda.device(self.device):
             if getattr(self, "_topk_key", None) != key:
@@ -93,6 +92,24 @@ class Engine:
             idx = torch.empty(B, k, dtype=torch.int64, device=self.device)
             cabi.check(self._lib.pbg_topk(self._h, _ptr(queries), B, int(k), _ptr(idx), _ptr(scores), self._stream()), self._h)
         return scores, idx
+
+    def topk_last_flagged(self) -> int:
+        """Rows of the last cosine_topk call (its last 16384-row chunk) that went to the exact scan; synchronises."""
+        return int(self._lib.pbg_topk_last_flagged(self._h, self._stream()))
+
+    MAX_TOP_K = 512   # include/pbg.h: pbg_topk selects up to 512 per row on the device
+
+    @classmethod
+    def validate_top_k(cls, k: int, num_rows: int) -> None:
+        """The errors of ``similarities.topk(k, dim=1)`` (pro_b_gan_infer.py:151, :236) plus this library's own limit,
+        raised on the host before anything is launched."""
+        if k > num_rows:
+            raise RuntimeError(f"selected index k out of range: k = {k} > {num_rows} rows")  # what torch.topk raises
+        if k < 1:
+            raise RuntimeError(f"top_k must be positive, got {k}")
+        if k > cls.MAX_TOP_K:
+            raise NotImplementedError(f"top_k = {k}: the CUDA path selects at most {cls.MAX_TOP_K} per row "
+                                      "(k <= 16 on the tensor-core filter, above that exact fp32 scores + selection)")
 
     def set_result_mirrors(self, gen_out=(), gen_scores=(), logits=(), probs=()) -> None:
         """Device addresses (ints) of up to 7 mirror buffers per result, e.g. peer GPUs' windows: every bf16-mode

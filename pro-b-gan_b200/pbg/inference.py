@@ -142,13 +142,18 @@ class FusedInference:
         pairs = self._stage_rows("pairs", head_relation_pairs, 2)
         out = (lambda t: t.cpu().numpy()) if as_arrays else (lambda t: t.tolist())
         B = pairs.shape[0]
+        self.engine.validate_top_k(top_k, self.num_entities)   # before anything is launched from the reused staging buffers
         with torch.no_grad(), torch.cuda.device(self.device):
-            dev_pairs = pairs.to(self.device, non_blocking=True)
-            z = self._latents(B).to(self.device, non_blocking=True)
-            pred = self.engine.generator_forward_gather(self.node_emb, self.rel_weight, dev_pairs[:, 0], dev_pairs[:, 1],
-                                                        z, precision=self.precision)
-            top_scores, top_idx = self.engine.cosine_topk(pred, self.node_emb, top_k)
-            self.engine.check_indices()
+            try:
+                dev_pairs = pairs.to(self.device, non_blocking=True)
+                z = self._latents(B).to(self.device, non_blocking=True)
+                pred = self.engine.generator_forward_gather(self.node_emb, self.rel_weight, dev_pairs[:, 0], dev_pairs[:, 1],
+                                                            z, precision=self.precision)
+                top_scores, top_idx = self.engine.cosine_topk(pred, self.node_emb, top_k)
+                self.engine.check_indices()
+            except BaseException:
+                torch.cuda.current_stream(self.device).synchronize()   # the copies out of the pinned buffers must not outlive the call
+                raise
             results: Dict[str, Any] = {
                 "predictions": out(top_idx),
                 "metadata": {"num_queries": B, "top_k": top_k, "model_hit10": self.best_val_hit10},
@@ -167,6 +172,7 @@ class FusedInference:
             "similar_entities": [],
             "metadata": {"num_queries": int(ids.numel()), "top_k": top_k, "model_hit10": self.best_val_hit10},
         }
+        self.engine.validate_top_k(top_k + 1, self.num_entities)
         with torch.no_grad(), torch.cuda.device(self.device):
             q = self.node_emb[ids.to(self.device)]
             top_scores, top_idx = self.engine.cosine_topk(q, self.node_emb, top_k + 1)

@@ -15,6 +15,8 @@ for p in (str(PKG), str(ROOT)):
         sys.path.insert(0, p)
 
 REFERENCE_SCRIPT = Path("/root/reference/pro_b_gan_infer.py")
+# the copy __graft_entry__.build() leaves for the GPU box (the reference mount does not exist there)
+REFERENCE_SCRIPT_COPY = ROOT / "oracle" / "_ref" / "pro_b_gan_infer.py"
 GOLDEN = ROOT / "tests" / "golden"
 
 

@@ -43,10 +43,25 @@ def test_topk_matches_reference_lines(dev, B, N, k):
     check(torch.randn(B, 128, generator=g), torch.randn(N, 128, generator=g), k, dev)
 
 
-def test_topk_large_k_and_other_width_take_the_exact_scan(dev):
+def test_topk_large_k_and_other_width_take_the_general_path(dev):
+    """k > 16 or E != 128: exact fp32 scores (SIMT GEMM over row chunks) + one selection CTA per row (k > 64
+    used to be refused and k = 17..64 scanned the table once per query)."""
     g = torch.Generator().manual_seed(5)
     check(torch.randn(50, 128, generator=g), torch.randn(3000, 128, generator=g), 40, dev, min_exact=0.5)  # k > 16 (41 gaps per row)
     check(torch.randn(33, 64, generator=g), torch.randn(2000, 64, generator=g), 10, dev)         # E != 128
+    check(torch.randn(300, 128, generator=g), torch.randn(65000, 128, generator=g), 64, dev, min_exact=0.3)
+    check(torch.randn(40, 128, generator=g), torch.randn(5000, 128, generator=g), 200, dev, min_exact=0.0)   # values only: 201 gaps per row
+    check(torch.randn(64, 256, generator=g), torch.randn(4096, 256, generator=g), 10, dev)       # the wide model's E
+    import modular_prot_b_gan as m
+    with pytest.raises(NotImplementedError):
+        m.cosine_topk(torch.randn(4, 128).to(dev), torch.randn(2000, 128).to(dev), 513)
+
+
+def test_topk_k16_on_the_filter_path_and_ragged_sizes(dev):
+    g = torch.Generator().manual_seed(21)
+    check(torch.randn(1000, 128, generator=g), torch.randn(65536, 128, generator=g), 16, dev)
+    check(torch.randn(257, 128, generator=g), torch.randn(4100, 128, generator=g), 3, dev)      # 17 tiles: 3 sample tiles
+    check(torch.randn(5, 128, generator=g), torch.randn(200001, 128, generator=g), 10, dev)
 
 
 def test_topk_near_duplicate_table_falls_back_to_the_exact_scan(dev):
