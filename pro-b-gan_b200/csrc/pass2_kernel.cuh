@@ -33,7 +33,7 @@
 #include <cuda.h>
 #include "ptx.cuh"
 #include "gather.cuh"
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 #include "pass_common.cuh"
 
 namespace pbg {
@@ -85,6 +85,7 @@ struct alignas(64) Pass2Params {
   unsigned layer_mask;
   int gather_defer;      // 1: a gather group's completion wait + arrival ride behind the next group's loads
   int gather_external;   // 1: xg0 / xd0 were written by a gather kernel before this launch (phase0_groups = 0)
+  int no_deps;           // 1: single-layer launch (pbg_linear_bf16): the A operand is the caller's, nothing to wait for
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
   int n_total;          // tickets of this launch
@@ -166,6 +167,7 @@ __device__ __forceinline__ uint32_t bias_leaky_pack(uint32_t a0, uint32_t a1, fl
 }
 
 __device__ __forceinline__ int p2_dep_target(const Pass2Params& p, int dep_kind) {
+  if (p.no_deps) return 0;
   if (dep_kind == DEP_X) return p.gather_external ? 0 : kP2GroupsPerBlock;
   const int producer = dep_kind == DEP_G0 ? IT_G_L0 : (dep_kind == DEP_D0 ? IT_D_L0 : IT_G_L1);
   return p.layer[producer].n_tiles * kP2WarpsPerPair;

@@ -4,7 +4,7 @@
 #include <cuda.h>
 #include "ptx.cuh"
 #include "gather.cuh"
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 
 namespace pbg {
 

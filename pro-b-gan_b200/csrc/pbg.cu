@@ -1,5 +1,5 @@
 // pbg.cu -- libpbg_b200.so: context, weight ingest, workspaces, TMA descriptors and the launch sequence behind
-// the C ABI declared in include/pbg.h.  Device code lives in gather.cuh / gemm_tc.cuh / gemm_f32.cuh.
+// the C ABI declared in include/pbg.h.  Device code lives in gather.cuh / pass2_kernel.cuh / topk_kernel.cuh / gemm_f32.cuh.
 //
 // HBM layout per ctx (sized lazily to the largest batch chunk seen, <= kMaxChunk rows):
 //   weights   : fp32 [out,in] + bias (parity mode) and bf16 [out_p, in_p] zero-padded to the tile grid + padded bias
@@ -25,7 +25,7 @@
 #include "../../include/pbg.h"
 #include "gather.cuh"
 #include "gemm_f32.cuh"
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 #include "pass_common.cuh"
 #include "pass2_kernel.cuh"
 #include "topk_kernel.cuh"
@@ -296,33 +296,6 @@ int ensure_stage(pbg_ctx* c, StageSlot& st, long long rows, cudaStream_t stream)
   PBG_TRY(make_tmap(c, &st.tm_xd0, st.xd0, cap, c->kd0p, kBlockM));
   st.cap = cap;
   return PBG_OK;
-}
-
-template <int BLOCK_N, int STAGES, int EPI>
-int launch_gemm_inst(pbg_ctx* c, int kind, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                     cudaStream_t s) {
-  using L = GemmSmem<BLOCK_N, STAGES>;
-  auto kern = gemm_bf16_tc_kernel<BLOCK_N, STAGES, EPI>;
-  static bool attr_set = false;  // per instantiation; ctxs on different devices share the function handle
-  static int attr_dev = -1;
-  if (!attr_set || attr_dev != c->dims.device) {
-    PBG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true; attr_dev = c->dims.device;
-  }
-  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
-  const int items = (EPI == EPI_LEAKY) ? m_tiles * (p.N / BLOCK_N) : m_tiles;
-  const int grid = std::max(1, std::min(items, c->num_sms));
-  { LaunchScope ls(c, kind, s);
-    kern<<<grid, kGemmThreads, L::kTotal, s>>>(ta, tb, p); }
-  PBG_CUDA(c, cudaGetLastError());
-  return PBG_OK;
-}
-
-template <int EPI>
-int launch_gemm(pbg_ctx* c, int kind, const Linear& l, const CUtensorMap& ta, GemmParams p, cudaStream_t s) {
-  p.N = l.np; p.K = l.kp; p.bias = l.b_pad; p.slope = c->dims.leaky_slope; p.trace = c->trace;
-  if (l.block_n == 256) return launch_gemm_inst<256, 4, EPI>(c, kind, ta, l.tmap_w, p, s);
-  return launch_gemm_inst<128, 6, EPI>(c, kind, ta, l.tmap_w, p, s);
 }
 
 template <int ACT>
@@ -1087,23 +1060,52 @@ int pbg_linear_bf16(pbg_ctx* c, int model, int layer, const void* a, void* out, 
   if (model == 0 && !c->g_loaded) return fail(c, PBG_ERR_NOT_LOADED, "generator weights not loaded");
   if (model == 1 && !c->d_loaded) return fail(c, PBG_ERR_NOT_LOADED, "discriminator weights not loaded");
   if (model < 0 || model > 1 || layer < 0 || layer > (model == 0 ? 2 : 1)) return fail(c, PBG_ERR_INVALID, "no such layer");
+  if (M > kMaxChunk) return fail(c, PBG_ERR_INVALID, "linear_bf16: at most %lld rows", kMaxChunk);
   PBG_CUDA(c, cudaSetDevice(c->dims.device));
-  const Linear& l = model == 0 ? c->g[layer] : c->d[layer];
-  CUtensorMap ta;
-  PBG_TRY(make_tmap(c, &ta, a, M, l.kp, kBlockM));
   cudaStream_t s = (cudaStream_t)stream;
-  GemmParams p{};
-  p.M = (int)M;
-  if (model == 0 && layer == 2) {
-    p.out = out; p.ldo = c->dims.embed_dim; p.n_valid = c->dims.embed_dim; p.out_f32 = 1;
-    return launch_gemm<EPI_TANH>(c, PBG_K_G_L2, l, ta, p, s);
+  PBG_TRY(ensure_ws(c, PBG_PREC_BF16, M, s));
+  Workspace& w = c->ws_bf16;
+  // ONE layer of the product kernel: the pass kernel with a single item kind, its A operand the caller's matrix and no
+  // dependency to wait for; the layer's own epilogue (LeakyReLU store / row dot + sigmoid / tanh) writes `out`.
+  static const int kind_of[2][3] = {{IT_G_L0, IT_G_L1, IT_G_L2}, {IT_D_L0, IT_D_L1, -1}};
+  static const int epi_of[5] = {PEPI_STORE, PEPI_STORE, PEPI_STORE, PEPI_ROWDOT, PEPI_TANH};
+  static const int pred_of[5] = {DEP_X, DEP_X, DEP_G0, DEP_D0, DEP_G1};
+  static const int out_of[5] = {DEP_G0, DEP_D0, DEP_G1, -1, -1};
+  const int k = kind_of[model][layer];
+  const Linear& l = model == 0 ? c->g[layer] : c->d[layer];
+  const int bn = (l.np % 256 == 0) ? 256 : 128;
+  Pass2Params p;
+  memset(&p, 0, sizeof p);
+  PBG_TRY(make_tmap(c, &p.tm_a[k], a, M, l.kp, kBlockM));
+  p.tm_w[k] = bn == 256 ? l.tmap_w128 : l.tmap_w64;
+  if (epi_of[k] == PEPI_STORE) PBG_TRY(make_tmap(c, &p.tm_o[k], out, M, l.np, 32));
+  p.layer[k] = P2Layer{l.kp / kBlockK, bn, l.np / bn, epi_of[k], pred_of[k], out_of[k], l.np, -1, l.b_pad,
+                       epi_of[k] == PEPI_STORE ? static_cast<__nv_bfloat16*>(out) : nullptr};
+  p.layer_mask = 1u << k;
+  const int nrb = static_cast<int>((M + kP2Rows - 1) / kP2Rows);
+  p.seg[0] = P2Segment{k, p.layer[k].n_tiles, 0, 0, k, 0};
+  p.n_seg = 1; p.n_total = nrb * p.layer[k].n_tiles;
+  p.no_deps = 1; p.gather_external = 1; p.phase0_groups = 0;
+  p.poll_ns = 40; p.gather_defer = 1;
+  p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(M); p.slope = c->dims.leaky_slope;
+  p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
+  p.part_g = w.part_g; p.part_d = w.part_d;
+  if (k == IT_G_L2) {
+    p.gen_out = out; p.out_f32 = 1; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
+    p.slots_g = (c->dims.embed_dim + 63) / 64;
   }
-  if (model == 1 && layer == 1) {
-    p.w3 = c->d_w3_pad; p.b3 = c->d_b3; p.logits = (float*)out;
-    return launch_gemm<EPI_ROWDOT>(c, PBG_K_D_L1, l, ta, p, s);
+  if (k == IT_D_L1) {
+    if (l.np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
+    p.w3 = c->d_w3_pad; p.b3 = c->d_b3; p.logits = static_cast<float*>(out); p.slots_d = l.np / 64;
   }
-  p.out = out; p.ldo = l.np; p.n_valid = l.np;
-  return launch_gemm<EPI_LEAKY>(c, model == 0 ? PBG_K_G_L0 + layer : PBG_K_D_L0 + layer, l, ta, p, s);
+  p.w3_off = -1;   // biases / final dot weights through the global path (BIASS = false instantiation)
+  const int grid = pass_grid(c) & ~1;
+  cudaError_t le;
+  { LaunchScope ls(c, model == 0 ? PBG_K_G_L0 + layer : PBG_K_D_L0 + layer, s);
+    le = launch_p2<false, false, false>(c, p, grid, s, false); }
+  if (le == cudaSuccess) le = cudaGetLastError();
+  if (le != cudaSuccess) return fail(c, PBG_ERR_CUDA, "single-layer pass launch failed: %s", cudaGetErrorString(le));
+  return PBG_OK;
 }
 
 int pbg_profile_enable(pbg_ctx* c, int enable) {

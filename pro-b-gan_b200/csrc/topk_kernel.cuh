@@ -26,7 +26,7 @@
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
-#include "gemm_tc.cuh"
+#include "tc_common.cuh"
 #include "pass_common.cuh"
 
 namespace pbg {

@@ -3,8 +3,10 @@
 The reference turns its inputs into tensors with ``json.loads`` (pro_b_gan_infer.py:485, :493, :501) followed by
 ``torch.tensor(list)`` (:135-136, :182, :226): ~70 ms of interpreter time at 32768 triplets in front of a 0.18 ms
 pass.  JSON text goes through ``pbg_parse_index_rows`` (C, one scan, no Python objects); lists go
-through numpy's C converter.  Like the reference, non-integer ids are an IndexError (it indexes with a float tensor,
-:139) and ragged rows a ValueError (``torch.tensor`` refuses them)."""
+through numpy's C converter.  Error types: in lists / arrays / tensors a non-integer id is an IndexError like the
+reference's (it indexes with a float tensor, :139) and ragged rows a ValueError (``torch.tensor`` refuses them); in
+JSON TEXT anything that is not a well-formed array of integers -- a float id, a ragged row, a stray token -- is a
+ValueError carrying the byte offset (the reference's json.loads would have accepted a float and failed later)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -101,7 +101,8 @@ def test_bf16_output_dtype_bf16(engine, oracle_models, tables, dev_tables, synth
 # ----------------------------------------------------------------------------- per-layer known answers
 @pytest.mark.parametrize("M", [1, 128, 200, 1000])
 def test_tensor_core_layers_known_answer(engine, cuda_models, dev, M):
-    """Each tcgen05 Linear against a torch fp32 product of the same bf16-rounded operands."""
+    """Each Linear of the PRODUCT kernel alone (pbg_linear_bf16 = the pass kernel with one item kind, its A operand the
+    caller's matrix) against a torch fp32 product of the same bf16-rounded operands."""
     G, D = cuda_models
     gl = [(w.to(dev), b.to(dev)) for w, b in G.folded_layers()]
     dl = [(w.to(dev), b.to(dev)) for w, b in D.folded_layers()]
