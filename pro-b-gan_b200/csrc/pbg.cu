@@ -792,8 +792,12 @@ int64_t pbg_topk_last_flagged(pbg_ctx* c, void* stream) {
   std::vector<int> h(static_cast<size_t>(t.last_rows));
   if (cudaMemcpyAsync(h.data(), t.flag, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return -1;
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
-  int64_t n = 0;
-  for (int v : h) n += v != 0;
+  int64_t n = 0, why[5] = {0, 0, 0, 0, 0};
+  for (int v : h) { n += v != 0; why[(v >= 0 && v <= 4) ? v : 0] += 1; }
+  char buf[160];
+  snprintf(buf, sizeof buf, "topk: %lld of %lld rows to the exact scan (list overflow %lld, too many candidates %lld, too few %lld, proof failed %lld)",
+           (long long)n, t.last_rows, (long long)why[1], (long long)why[2], (long long)why[3], (long long)why[4]);
+  c->err = buf;   // diagnostics text, readable through pbg_last_error
   return n;
 }
 

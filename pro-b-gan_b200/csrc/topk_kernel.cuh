@@ -32,7 +32,7 @@
 namespace pbg {
 
 constexpr int kTkStages = 4;          // entity tiles in flight per CTA (32 KB each: 128 entities x 128 dims bf16)
-constexpr int kTkCand = 160;          // (group, mask) entries kept per (row, entity range, column half), in global memory
+constexpr int kTkCand = 256;          // (group, mask) entries kept per (row, entity range, column half), in global memory
 constexpr int kTkMaxRanges = 16;
 constexpr int kTkMaxK = 16;           // largest k of the filter path; above it the general path runs
 constexpr int kTkSampleStride = 8;    // every 8th 256-entity tile is sampled for the cut-off
@@ -292,8 +292,12 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
   }
 }
 
-// One warp per query row: tau = the k-th largest of the row's sampled group keys (n_lists x kTkKeys of them), with its
-// position bits cleared -- at least k sampled entities score >= tau.  Fewer than k positive keys: tau = 0.
+// One warp per query row: s_k = the k-th largest of the row's sampled group keys (n_lists x kTkKeys of them) with its
+// position bits cleared -- at least k sampled entities have a bf16 score >= s_k, hence an exact score >= s_k - err, so
+// the k-th exact score of the row is >= s_k - err.  The scan's cut-off is tau = s_k - 2 err - 1e-4: every entity that is
+// NOT marked has a bf16 score <= tau, i.e. an exact score <= tau + err < s_k - err <= the k-th exact score -- the proof
+// obligation of the rescoring kernel holds by construction (it is still checked), at the price of about a dozen more
+// candidates per row than a cut-off at s_k itself.  Fewer than k positive keys: tau = 0.
 __global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ samp_keys, int n_lists, long long B, long long rows_pad,
                                                        int k, float* __restrict__ tau) {
   const int lane = threadIdx.x & 31;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ s
     }
     kth = wbest;
   }
-  if (lane == 0) tau[row] = kth > 0 ? __int_as_float(kth & ~0x1F) : 0.f;
+  if (lane == 0) tau[row] = kth > 0 ? fmaxf(__int_as_float(kth & ~0x1F) - (2.f * kTkErrBound + 1e-4f), 0.f) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ 4. rescore
@@ -336,59 +340,83 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restri
                                                            int n_lists, long long B, long long N, int k,
                                                            long long* __restrict__ out_idx, float* __restrict__ out_score,
                                                            int* __restrict__ flag) {
-  __shared__ float qn_s[8][128];
   __shared__ float es_s[8][kTkRescoreMax];
   __shared__ int ei_s[8][kTkRescoreMax];
-  __shared__ int cnt_s[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  float* qn = qn_s[w]; float* es = es_s[w]; int* ei = ei_s[w];
+  float* es = es_s[w]; int* ei = ei_s[w];
   const long long row = static_cast<long long>(blockIdx.x) * 8 + w;
   if (row >= B) return;
+  // this lane's four dimensions of the normalised query stay in registers
+  float4 qv = *reinterpret_cast<const float4*>(q + row * 128 + 4 * lane);
   {
     const float iq = inv_q[row];
-    float4 v = *reinterpret_cast<const float4*>(q + row * 128 + 4 * lane);
-    v.x *= iq; v.y *= iq; v.z *= iq; v.w *= iq;
-    *reinterpret_cast<float4*>(qn + 4 * lane) = v;
+    qv.x *= iq; qv.y *= iq; qv.z *= iq; qv.w *= iq;
   }
-  if (lane == 0) cnt_s[w] = 0;
-  __syncwarp();
-  // decode: lane l walks list l (n_lists <= 32)
-  bool bad = false;
-  if (lane < n_lists) {
-    const long long lb = row * n_lists + lane;
-    const int c = cand_cnt[lb];
-    bad = c > kTkCand;
-    for (int e = 0; e < min(c, kTkCand); ++e) {
-      const unsigned g = cand_grp[lb * kTkCand + e];
-      unsigned mk = cand_mask[lb * kTkCand + e];
-      while (mk != 0u) {
-        const int b = __ffs(mk) - 1;
-        mk &= mk - 1u;
-        const long long ent = static_cast<long long>(g) * 32 + (31 - b);   // the scan shifts score j in at bit 31 - j
-        if (ent < N) {
-          const int pos = atomicAdd(&cnt_s[w], 1);
-          if (pos < kTkRescoreMax) ei[pos] = static_cast<int>(ent);
-        }
+  // decode: the row's lists are one flat sequence of (group, mask) entries (list l = lane l's count, a shuffle prefix
+  // sum gives every list's offset); 32 entries per round, one per lane, all their loads in flight together; the set
+  // bits are compacted into ei[] in (entry, bit) order with a ballot per round -- deterministic, no atomics
+  int c_l = lane < n_lists ? cand_cnt[row * n_lists + lane] : 0;
+  const bool overflow = __any_sync(0xffffffffu, c_l > kTkCand);
+  c_l = min(c_l, kTkCand);
+  int pre = c_l;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+  const int total = __shfl_sync(0xffffffffu, pre, 31);
+  const int start = pre - c_l;
+  int ncand = 0;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    int l = 0, st = 0;
+    for (int ll = 0; ll < n_lists; ++ll) {
+      const int pe = __shfl_sync(0xffffffffu, pre, ll), ps = __shfl_sync(0xffffffffu, start, ll);
+      if (i >= ps && i < pe) { l = ll; st = ps; }
+    }
+    unsigned g = 0u, mk = 0u;
+    if (i < total) {
+      const long long at = (row * n_lists + l) * kTkCand + (i - st);
+      g = cand_grp[at]; mk = cand_mask[at];
+    }
+    while (__any_sync(0xffffffffu, mk != 0u)) {
+      const bool has = mk != 0u;
+      const unsigned who = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int b = 31 - __clz(mk);                 // highest bit first = lowest score index j first (bit 31 - j)
+        mk &= ~(1u << b);
+        const long long ent = static_cast<long long>(g) * 32 + (31 - b);
+        const int pos = ncand + __popc(who & ((1u << lane) - 1u));
+        if (pos < kTkRescoreMax) ei[pos] = ent < N ? static_cast<int>(ent) : -1;
       }
+      ncand += __popc(who);
     }
   }
   __syncwarp();
-  const int ncand_all = cnt_s[w];
-  bad = __any_sync(0xffffffffu, bad) || ncand_all > kTkRescoreMax || ncand_all < k;
-  if (bad) { if (lane == 0) flag[row] = 1; return; }
-  const int ncand = ncand_all;
-  for (int c = lane; c < ncand; c += 32) {
-    const int idx = ei[c];
-    const float it = inv_t[idx];
-    const float4* tr = reinterpret_cast<const float4*>(table + static_cast<long long>(idx) * 128);
-    float d = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const float4 tv = __ldg(tr + j);
-      const float4 qv = *reinterpret_cast<const float4*>(qn + 4 * j);
-      d += qv.x * (tv.x * it) + qv.y * (tv.y * it) + qv.z * (tv.z * it) + qv.w * (tv.w * it);
+  // flag values (any non-zero value sends the row to the exact scan): 1 a list overflowed, 2 too many candidates,
+  // 3 fewer than k candidates, 4 the proof failed
+  const int why = overflow ? 1 : (ncand > kTkRescoreMax ? 2 : (ncand < k ? 3 : 0));
+  if (why) { if (lane == 0) flag[row] = why; return; }
+  // exact scores: the whole warp on one candidate -- its 512-byte row in ONE coalesced load -- sixteen candidates (8 KB of
+  // row reads) in flight per warp
+  constexpr int U = 16;
+  for (int c0 = 0; c0 < ncand; c0 += U) {
+    float d[U]; int id[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) id[u] = c0 + u < ncand ? ei[c0 + u] : -1;
+    float4 tv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      tv[u] = id[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(table + static_cast<long long>(id[u]) * 128) + lane)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < U; ++u) d[u] = qv.x * tv[u].x + qv.y * tv[u].y + qv.z * tv[u].z + qv.w * tv[u].w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
     }
-    es[c] = d;
+    float dv = d[0]; int iv = id[0];
+#pragma unroll
+    for (int u = 1; u < U; ++u) if (lane == u) { dv = d[u]; iv = id[u]; }
+    if (lane < U && c0 + lane < ncand) es[c0 + lane] = iv >= 0 ? dv * inv_t[iv] : -3.0e38f;
   }
   __syncwarp();
   float kth = -3.0e38f;
@@ -413,7 +441,7 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restri
     __syncwarp();
   }
   // nothing outside the candidate set can reach the k-th exact score: its bf16 score is <= tau
-  if (lane == 0) flag[row] = (kth > tau[row] + kTkErrBound) ? 0 : 1;
+  if (lane == 0) flag[row] = (kth > tau[row] + kTkErrBound) ? 0 : 4;
 }
 
 // Exact selection, one CTA per row: every thread keeps the k best of its entities, the CTA merges (k rounds of a block

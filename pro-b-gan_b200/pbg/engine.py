@@ -95,7 +95,9 @@ class Engine:
 
     def topk_last_flagged(self) -> int:
         """Rows of the last cosine_topk call (its last 16384-row chunk) that went to the exact scan; synchronises."""
-        return int(self._lib.pbg_topk_last_flagged(self._h, self._stream()))
+        n = int(self._lib.pbg_topk_last_flagged(self._h, self._stream()))
+        self.topk_flag_report = cabi.last_error(self._h)    # "… rows to the exact scan (list overflow a, …, proof failed d)"
+        return n
 
     MAX_TOP_K = 512   # include/pbg.h: pbg_topk selects up to 512 per row on the device
 

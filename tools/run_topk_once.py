@@ -12,4 +12,5 @@ q, t = torch.randn(B, 128, generator=g).to(dev), torch.randn(65536, 128, generat
 for _ in range(4):
     s, i = m.cosine_topk(q, t, 10)
 torch.cuda.synchronize()
-print("ok", float(s.sum()))
+eng = m._TOPK_ENGINES[(0, 128)]
+print("ok", float(s.sum()), "flagged:", eng.topk_last_flagged(), eng.topk_flag_report)
