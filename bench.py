@@ -29,7 +29,7 @@ Timed region (SURVEY.md 8d "steady state: >= 100 back-to-back forward calls"; VE
 
 Printed JSON (one line, rank 0):
   value      samples/s, whole job, inputs resident in HBM, CUDA events, max over ranks
-  e2e        same metric through the C-ABI host entry point pbg_score_triplets_host (synchronous), one host thread
+  e2e        same metric through the C-ABI host entry point pbg_score_triplets_host_packed (synchronous), one host thread
              per lane: per step H2D of the triplets + latents from pinned host memory and D2H of what the
              reference's score_triplets returns (pro_b_gan_infer.py:204-209)
   roofline   dominant kernel vs the measured bf16 tensor peak (MEASURED_PEAKS.json)
@@ -529,9 +529,13 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     import threading
     hp = []
     for i in range(min(P, 16 * S)):
-        trip = synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=9000 + i)[lo:hi].contiguous().pin_memory()
-        z = synth.make_latents(Bg, Z, seed=9500 + i)[lo:hi].contiguous().pin_memory()
-        hp.append((trip, z))
+        # one pinned block per request, [triplets int64 B x 3 | latents fp32 B x Z]: adjacent buffers go in one H2D copy
+        blk = torch.empty(B * (3 * 8 + Z * 4), dtype=torch.uint8).pin_memory()
+        trip = blk[:B * 24].view(torch.int64).view(B, 3)
+        z = blk[B * 24:].view(torch.float32).view(B, Z)
+        trip.copy_(synth.make_triplets(Bg, NUM_ENTITIES, NUM_RELATIONS, seed=9000 + i)[lo:hi])
+        z.copy_(synth.make_latents(Bg, Z, seed=9500 + i)[lo:hi])
+        hp.append(blk)
     # a synchronous call spends most of its life in PCIe copies and the completion wake-up, so the server model is
     # more calls in flight than passes fit on the device: T host threads (default one per lane; --e2e-threads), one ctx each
     T = args.e2e_threads if args.e2e_threads > 0 else S
@@ -539,15 +543,14 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
         e.set_result_mirrors()   # host results need no re-assembly: every rank's caller receives its own shard
         e.set_result_multicast()
     e2e_engines = engines + [m.make_fused_engine(G, D, ctas=widths[i % S]) for i in range(max(0, T - S))]
-    h_out = [(None, torch.empty(B).pin_memory(), torch.empty(B).pin_memory(), torch.empty(B).pin_memory())
-             for _ in range(T)]  # score_triplets returns scores / logits / probabilities, not the predicted embeddings
+    # score_triplets returns scores / logits / probabilities, not the predicted embeddings; one pinned block per thread
+    # [scores | logits | probs]: one D2H copy
+    h_blocks = [torch.empty(3 * B).pin_memory() for _ in range(T)]
 
     def e2e_worker(lane: int, first: int, last: int):
         torch.cuda.set_device(local_rank)
-        h_gen, h_sc, h_lg, h_pb = h_out[lane]
         for i in range(first + lane, last, T):
-            trip, z = hp[i % len(hp)]
-            e2e_engines[lane].score_triplets_host(node_emb, rel_w, trip, z, h_gen, h_sc, h_lg, h_pb, precision="bf16")
+            e2e_engines[lane].score_triplets_host_packed(node_emb, rel_w, hp[i % len(hp)], h_blocks[lane], B, precision="bf16")
 
     def e2e_run(first: int, last: int) -> float:
         ts = [threading.Thread(target=e2e_worker, args=(lane, first, last)) for lane in range(T)]
@@ -572,7 +575,7 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     e2e = {"value": Bg * Ke / e2e_s, "unit": "samples/s",
            "h2d_bytes_per_step": B * (3 * 8 + Z * 4) * world, "d2h_bytes_per_step": B * 3 * 4 * world,
            "steps": Ke, "seconds": e2e_s,
-           "api": f"pbg_score_triplets_host (C ABI, pinned host buffers, one sync per call), "
+           "api": f"pbg_score_triplets_host_packed (C ABI, pinned host blocks [triplets | z] in and [scores | logits | probs] out: one copy per direction, one sync per call), "
                   f"{T} host thread(s), one ctx each; wall clock over {Ke} calls (>= --steps, long enough for "
                   f"{args.e2e_min_s} s)"}
 

@@ -123,11 +123,22 @@ int pbg_score_triplets(pbg_ctx* ctx, const float* node_emb, int64_t N, const flo
 /* Same pass with HOST index / latent / result buffers: the end-to-end form the reference's
  * list API implies (H2D at :182, D2H at :203, :208-209).  node_emb / rel_emb stay device
  * pointers (they are model state moved once at load, :83, :102).  Synchronous.  Returns
- * PBG_ERR_INDEX if any id is out of range (results are then undefined). */
+ * PBG_ERR_INDEX if any id is out of range (results are then undefined).  Pinned (page-locked) host memory keeps
+ * the copies asynchronous. */
 int pbg_score_triplets_host(pbg_ctx* ctx, const float* node_emb, int64_t N, const float* rel_emb,
                             int64_t R, const int64_t* triplets_host, const float* z_host,
                             float* gen_out_host, float* gen_scores_host, float* logits_host,
                             float* probs_host, int64_t B, int precision);
+
+/* The same call for a caller that packs a request into two host blocks (each ONE allocation):
+ *   in_block_host  = [ triplets int64 B x 3 | z fp32 B x Z ]          (24 B + 4 Z B bytes)
+ *   out_block_host = [ gen_scores | logits | probs ] fp32 B each      (12 B bytes)
+ * Each block travels in ONE copy (a DMA operation costs microseconds of set-up beside its bytes: six of them were
+ * a third of a 4096-triplet call; for an odd B the latents are not 16-byte aligned behind the triplets and the
+ * inputs go in two copies).  Generator + discriminator both run.  Otherwise as pbg_score_triplets_host. */
+int pbg_score_triplets_host_packed(pbg_ctx* ctx, const float* node_emb, int64_t N, const float* rel_emb,
+                                   int64_t R, const void* in_block_host, float* out_block_host, int64_t B,
+                                   int precision);
 
 /* Request staging -- the ingest / compute split of the same pass for callers that keep requests in flight.
  * pbg_score_triplets does gather -> layers in one launch, so the first tiles of every pass wait for its gather.

@@ -114,8 +114,10 @@ struct pbg_ctx {
   int* err_flag = nullptr;       // device
   int* err_flag_host = nullptr;  // pinned
   cudaStream_t own_stream = nullptr;
-  // device staging for the *_host entry point
+  // device staging for the *_host entry point: ONE block [triplets | z | scores | logits | probs | gen_out], so that
+  // host buffers the caller laid out the same way travel in one copy per direction
   long long host_cap = 0;
+  char* st_block = nullptr;
   long long* st_trip = nullptr;
   float *st_z = nullptr, *st_gen = nullptr, *st_scores = nullptr, *st_logits = nullptr, *st_probs = nullptr;
   EncodeTiledFn encode = nullptr;
@@ -412,7 +414,7 @@ cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s
     attr_dev = c->dims.device;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kPassThreads); cfg.dynamicSmemBytes = P2Smem::kTotal; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kP2Threads); cfg.dynamicSmemBytes = P2Smem::kTotal; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -562,7 +564,7 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
     cudaFuncAttributes fa{};
     cudaFuncGetAttributes(&fa, pbg_pass2_kernel<false, true, true>);
     return fail(c, PBG_ERR_CUDA, "pass kernel launch failed: %s (grid %d x %d threads, %d regs/thread, %zu B static + %d B dynamic smem, "
-                "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kPassThreads, fa.numRegs,
+                "max threads/block %d, max dynamic smem %d)", cudaGetErrorString(le), grid, kP2Threads, fa.numRegs,
                 fa.sharedSizeBytes, P2Smem::kTotal, fa.maxThreadsPerBlock, fa.maxDynamicSharedSizeBytes);
   }
   return PBG_OK;
@@ -895,8 +897,7 @@ void pbg_destroy(pbg_ctx* c) {
   cudaFree(c->tk.samp_keys); cudaFree(c->tk.tau); cudaFree(c->tk.score_buf);
 
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
-  cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
-  cudaFree(c->st_logits); cudaFree(c->st_probs);
+  cudaFree(c->st_block);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -1166,9 +1167,12 @@ int pbg_check_indices(pbg_ctx* c, void* stream) {
   return PBG_OK;
 }
 
-int pbg_score_triplets_host(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
-                            const int64_t* triplets_host, const float* z_host, float* gen_out_host,
-                            float* gen_scores_host, float* logits_host, float* probs_host, int64_t B, int precision) {
+namespace {
+// Shared body of the *_host entry points.  packed: the caller's buffers are TWO blocks -- in_block = [triplets int64
+// B x 3 | z fp32 B x Z], out_block = [gen_scores | logits | probs] fp32 B each -- and travel in one copy per direction.
+int score_host(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R, const int64_t* triplets_host,
+               const float* z_host, float* gen_out_host, float* gen_scores_host, float* logits_host, float* probs_host,
+               int64_t B, int precision, bool packed) {
   if (!c) return PBG_ERR_INVALID;
   if (B < 0) return fail(c, PBG_ERR_INVALID, "negative batch");
   if (B == 0) return PBG_OK;
@@ -1179,29 +1183,64 @@ int pbg_score_triplets_host(pbg_ctx* c, const float* node_emb, int64_t N, const 
   const int E = c->dims.embed_dim, Z = c->dims.noise_dim;
   if (c->host_cap < B) {
     PBG_CUDA(c, cudaDeviceSynchronize());
-    cudaFree(c->st_trip); cudaFree(c->st_z); cudaFree(c->st_gen); cudaFree(c->st_scores);
-    cudaFree(c->st_logits); cudaFree(c->st_probs);
-    c->st_trip = nullptr; c->st_z = c->st_gen = c->st_scores = c->st_logits = c->st_probs = nullptr;
-    c->host_cap = 0;
-    PBG_CUDA(c, cudaMalloc(&c->st_trip, sizeof(long long) * 3 * B));
-    PBG_CUDA(c, cudaMalloc(&c->st_z, sizeof(float) * Z * B));
-    PBG_CUDA(c, cudaMalloc(&c->st_gen, sizeof(float) * E * B));
-    PBG_CUDA(c, cudaMalloc(&c->st_scores, sizeof(float) * B));
-    PBG_CUDA(c, cudaMalloc(&c->st_logits, sizeof(float) * B));
-    PBG_CUDA(c, cudaMalloc(&c->st_probs, sizeof(float) * B));
+    cudaFree(c->st_block); c->st_block = nullptr; c->host_cap = 0;
+    const size_t per_row = sizeof(long long) * 3 + sizeof(float) * (Z + 3 + E);
+    PBG_CUDA(c, cudaMalloc(&c->st_block, per_row * B + 64));   // + alignment padding in front of z and gen_out
     c->host_cap = B;
   }
+  {
+    // one device block, laid out for THIS call's B: [triplets | z | scores | logits | probs | gen_out]; z and gen_out rows
+    // are read / written with 16-byte vectors, so their offsets are rounded up
+    auto up16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
+    char* b0 = c->st_block;
+    size_t off = 0;
+    c->st_trip = reinterpret_cast<long long*>(b0 + off);  off = up16(off + sizeof(long long) * 3 * B);
+    c->st_z = reinterpret_cast<float*>(b0 + off);         off += sizeof(float) * Z * B;
+    c->st_scores = reinterpret_cast<float*>(b0 + off);    off += sizeof(float) * B;
+    c->st_logits = reinterpret_cast<float*>(b0 + off);    off += sizeof(float) * B;
+    c->st_probs = reinterpret_cast<float*>(b0 + off);     off = up16(off + sizeof(float) * B);
+    c->st_gen = reinterpret_cast<float*>(b0 + off);
+  }
   cudaStream_t s = c->own_stream;
-  PBG_CUDA(c, cudaMemcpyAsync(c->st_trip, triplets_host, sizeof(long long) * 3 * B, cudaMemcpyHostToDevice, s));
-  if (run_g) PBG_CUDA(c, cudaMemcpyAsync(c->st_z, z_host, sizeof(float) * Z * B, cudaMemcpyHostToDevice, s));
+  // every DMA operation costs a few microseconds of set-up beside its bytes (six of them were a third of a 4096-triplet
+  // call): the packed form moves [triplets | z] and [scores | logits | probs] in one copy each
+  const bool one_h2d = packed && reinterpret_cast<char*>(c->st_z) == reinterpret_cast<char*>(c->st_trip) + sizeof(long long) * 3 * B;
+  if (one_h2d) {
+    PBG_CUDA(c, cudaMemcpyAsync(c->st_trip, triplets_host, sizeof(long long) * 3 * B + sizeof(float) * Z * B, cudaMemcpyHostToDevice, s));
+  } else {
+    PBG_CUDA(c, cudaMemcpyAsync(c->st_trip, triplets_host, sizeof(long long) * 3 * B, cudaMemcpyHostToDevice, s));
+    if (run_g) PBG_CUDA(c, cudaMemcpyAsync(c->st_z, z_host, sizeof(float) * Z * B, cudaMemcpyHostToDevice, s));
+  }
   PBG_TRY(pbg_score_triplets(c, node_emb, N, rel_emb, R, (const int64_t*)c->st_trip, run_g ? c->st_z : nullptr,
                              gen_out_host ? c->st_gen : nullptr, PBG_DT_F32, gen_scores_host ? c->st_scores : nullptr,
                              logits_host ? c->st_logits : nullptr, probs_host ? c->st_probs : nullptr, B, precision, s));
+  if (packed) {
+    PBG_CUDA(c, cudaMemcpyAsync(gen_scores_host, c->st_scores, sizeof(float) * 3 * B, cudaMemcpyDeviceToHost, s));
+  } else {
+    if (gen_scores_host) PBG_CUDA(c, cudaMemcpyAsync(gen_scores_host, c->st_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+    if (logits_host) PBG_CUDA(c, cudaMemcpyAsync(logits_host, c->st_logits, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+    if (probs_host) PBG_CUDA(c, cudaMemcpyAsync(probs_host, c->st_probs, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
+  }
   if (gen_out_host) PBG_CUDA(c, cudaMemcpyAsync(gen_out_host, c->st_gen, sizeof(float) * E * B, cudaMemcpyDeviceToHost, s));
-  if (gen_scores_host) PBG_CUDA(c, cudaMemcpyAsync(gen_scores_host, c->st_scores, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
-  if (logits_host) PBG_CUDA(c, cudaMemcpyAsync(logits_host, c->st_logits, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
-  if (probs_host) PBG_CUDA(c, cudaMemcpyAsync(probs_host, c->st_probs, sizeof(float) * B, cudaMemcpyDeviceToHost, s));
   return pbg_check_indices(c, s);  // one sync: results + the out-of-range flag
+}
+}  // namespace
+
+int pbg_score_triplets_host(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                            const int64_t* triplets_host, const float* z_host, float* gen_out_host,
+                            float* gen_scores_host, float* logits_host, float* probs_host, int64_t B, int precision) {
+  return score_host(c, node_emb, N, rel_emb, R, triplets_host, z_host, gen_out_host, gen_scores_host, logits_host, probs_host, B,
+                    precision, false);
+}
+
+int pbg_score_triplets_host_packed(pbg_ctx* c, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                                   const void* in_block_host, float* out_block_host, int64_t B, int precision) {
+  if (!c) return PBG_ERR_INVALID;
+  if (B > 0 && (!in_block_host || !out_block_host)) return fail(c, PBG_ERR_INVALID, "null block");
+  const int64_t* trip = static_cast<const int64_t*>(in_block_host);
+  const float* z = reinterpret_cast<const float*>(static_cast<const char*>(in_block_host) + sizeof(long long) * 3 * B);
+  return score_host(c, node_emb, N, rel_emb, R, trip, z, nullptr, out_block_host, out_block_host + B, out_block_host + 2 * B, B,
+                    precision, true);
 }
 
 }  // extern "C"

@@ -387,3 +387,18 @@ class Engine:
                 self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(triplets_host),
                 _ptr(z_host), _ptr(gen_out_host), _ptr(gen_scores_host), _ptr(logits_host), _ptr(probs_host),
                 B, precision_code(precision)), self._h)
+
+    def score_triplets_host_packed(self, node_emb, rel_w, in_block_host: torch.Tensor, out_block_host: torch.Tensor,
+                                   B: int, precision=None) -> None:
+        """pbg_score_triplets_host_packed: ``in_block_host`` = uint8 [24 B + 4 Z B] holding [triplets int64 | z fp32],
+        ``out_block_host`` = fp32 [3 B] receiving [gen_scores | logits | probs]; one copy per direction, one sync."""
+        if in_block_host.device.type != "cpu" or out_block_host.device.type != "cpu":
+            raise ValueError("the blocks must be CPU (ideally pinned) tensors")
+        if in_block_host.numel() * in_block_host.element_size() != B * (24 + 4 * self.Z) or not in_block_host.is_contiguous():
+            raise ValueError(f"in_block_host must hold {B * (24 + 4 * self.Z)} contiguous bytes")
+        if out_block_host.dtype != torch.float32 or out_block_host.numel() != 3 * B or not out_block_host.is_contiguous():
+            raise ValueError(f"out_block_host must be a contiguous fp32 tensor of {3 * B} elements")
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_score_triplets_host_packed(
+                self._h, _ptr(node_emb), node_emb.shape[0], _ptr(rel_w), rel_w.shape[0], _ptr(in_block_host),
+                _ptr(out_block_host), B, precision_code(precision)), self._h)

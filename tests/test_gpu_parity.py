@@ -539,3 +539,27 @@ def test_stress_ragged_sizes_on_concurrent_lanes_bit_identical(cuda_models, dev_
     for e in engines:
         e.check_indices()
     assert n >= 200
+
+
+# ----------------------------------------------------------------------------- host entry points
+@pytest.mark.parametrize("B", [4096, 333])
+def test_host_entry_points_packed_and_per_buffer(engine, dev_tables, synth, dev, B):
+    """pbg_score_triplets_host_packed moves [triplets | z] and [scores | logits | probs] in one copy each (an odd B: z is
+    not 16-byte aligned behind the triplets, the inputs go in two copies); pbg_score_triplets_host copies buffer by
+    buffer.  Same results either way, equal to the device-pointer call."""
+    trip, z = synth.make_triplets(B, seed=31), synth.make_latents(B, seed=32)
+    ref = _pass(engine, dev_tables, trip.to(dev), z.to(dev))
+    blk = torch.empty(B * (24 + 64 * 4), dtype=torch.uint8).pin_memory()
+    blk[:B * 24].view(torch.int64).view(B, 3).copy_(trip)
+    blk[B * 24:].view(torch.float32).view(B, 64).copy_(z)
+    hb = torch.zeros(3 * B).pin_memory()
+    engine.score_triplets_host_packed(*dev_tables, blk, hb, B, precision="bf16")
+    sep = [torch.zeros(B).pin_memory() for _ in range(3)]
+    gen = torch.zeros(B, 128).pin_memory()
+    engine.score_triplets_host(*dev_tables, trip.clone().pin_memory(), z.clone().pin_memory(), gen, *sep, precision="bf16")
+    for i, k in enumerate(("gen_scores", "logits", "probs")):
+        assert torch.equal(hb[i * B:(i + 1) * B], ref[k].cpu()), k
+        assert torch.equal(sep[i], ref[k].cpu()), k
+    assert torch.equal(gen.bfloat16(), ref["gen_out"].cpu())   # the host form returns fp32 rows of the same values
+    with pytest.raises(ValueError):
+        engine.score_triplets_host_packed(*dev_tables, blk[:-8], hb, B)
