@@ -191,3 +191,27 @@ def test_bench_reference_arm_under_torchrun_prints_one_line_from_rank_0():
     assert len(lines) == 1, out.stdout
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
+def test_top_k_is_validated_on_the_host_before_anything_is_launched():
+    """torch.topk's own error for k > rows (pro_b_gan_infer.py:151 raises RuntimeError), and this library's limit."""
+    from pbg.engine import Engine
+    Engine.validate_top_k(10, 65536)
+    Engine.validate_top_k(512, 65536)
+    with pytest.raises(RuntimeError, match="out of range"):
+        Engine.validate_top_k(11, 10)
+    with pytest.raises(RuntimeError):
+        Engine.validate_top_k(0, 10)
+    with pytest.raises(NotImplementedError, match="512"):
+        Engine.validate_top_k(513, 65536)
+
+
+def test_bench_flop_and_config_table_match_the_survey():
+    """bench.py's algorithmic flop counts are SURVEY.md 8d's (2*K*N per Linear) for both BASELINE model shapes."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", str(ROOT / "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.flops_per_sample(128, 64, 1024) == (3014656, 1836032)
+    assert bench.flops_per_sample(256, 64, 4096) == (40370176, 23072768)
+    assert bench.CONFIGS["base"]["batch"] == 4096 and bench.CONFIGS["wide"]["batch"] == 1024
