@@ -9,15 +9,17 @@
 // (M = 256: 128 rows of A per CTA; the BLOCK_N rows of W are split in halves, one per CTA), so a 64-deep k-block
 // costs each SM 16 KB of A + 16 KB of W (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for a single-CTA
 // 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).  This main
-// loop alone sustains 546 clk per k-block on all 148 SMs (floor 512; tools/ubench_pipe.cu).
+// loop alone sustains 546 clk per k-block on all 148 SMs with constant operands (floor 512; tools/ubench_pipe.cu); with real
+// operands and the rest of the chip busy it runs at ~756, the rate of the measured cuBLAS burst peak.
 //
 //   leader CTA (cluster rank 0)                               peer CTA (rank 1)
-//   warp 0   TMA producer for its halves of A and W           warp 0   TMA producer for its halves of A and W,
+//   warps 0..7  epilogue of its 128 rows / gather groups      warps 0..7  epilogue of its 128 rows / gather groups
+//   warp 8   TMA producer for its halves of A and W           warp 8   TMA producer for its halves of A and W,
 //                                                                      signalling the leader's full barriers
-//   warp 1   MMA issuer (one thread) for the pair             warp 1   scheduler (one thread): pops tickets up to a
+//   warp 9   MMA issuer (one thread) for the pair             warp 9   scheduler (one thread): pops tickets up to a
 //                                                                      ring's depth ahead, waits for the item's input
 //                                                                      row block, publishes the item to both CTAs
-//   warps 2..9  epilogue of its 128 rows / gather items       warps 2..9  epilogue of its 128 rows / gather items
+//   (PBG_ROLES_FIRST=1 puts the two single-thread roles in warps 0 / 1, the round-1 layout; measured neutral)
 //
 // Tickets index a static, topologically ordered item list described by a few segments in the kernel parameters
 // (layer by layer, row-block major).  A pair takes its tickets in order from one atomic counter and works through

@@ -464,10 +464,9 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   }
   if (on[IT_D_L1] && lin[IT_D_L1]->np / 64 > kPartSlotsD) return fail(c, PBG_ERR_UNSUPPORTED, "d_hidden too wide for the partial buffer");
   if (on[IT_G_L2] && lin[IT_G_L2]->np / 64 > kPartSlotsG / 2) return fail(c, PBG_ERR_UNSUPPORTED, "embed_dim too wide for the partial buffer");
-  // phase 0: the first row blocks are gathered by the epilogue warps of all CTAs before the roles start (one 4-row
-  // group per warp); the rest of the batch goes through gather items (64 rows each)
-  // phase 0 gathers every row (4-row groups, statically spread over the epilogue warps of the grid); every tile is
-  // a static ticket, layer by layer (a topological order): the producers poll the dependency counters.
+  // The gather ("phase 0"): every row of the pass in 4-row groups that the epilogue warps claim from a counter -- one
+  // group each up front, the rest whenever a warp would otherwise wait (pass2_kernel.cuh).  Every tile is a static
+  // ticket, layer by layer (a topological order); the scheduler thread polls a ticket's dependency counter.
   p.phase0_groups = external_gather ? 0 : nrb * kP2GroupsPerBlock;
   p.gather_external = external_gather ? 1 : 0;
   {
