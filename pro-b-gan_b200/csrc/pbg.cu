@@ -635,7 +635,8 @@ int pbg_topk_prepare(pbg_ctx* c, const float* table, int64_t N, void* stream) {
   }
   t.table = table; t.N = N;
   { LaunchScope ls(c, PBG_K_OTHER, s);
-    topk_prepare_kernel<<<c->num_sms * 8, 256, 0, s>>>(table, N, n_pad, E, t.tn, t.inv_t); }
+    if (E <= 128) topk_prepare_kernel<8, 1><<<c->num_sms * 8, 256, 0, s>>>(table, N, n_pad, E, t.tn, t.inv_t);
+    else topk_prepare_kernel<2, 4><<<c->num_sms * 8, 256, 0, s>>>(table, N, n_pad, E, t.tn, t.inv_t); }
   PBG_CUDA(c, cudaGetLastError());
   return PBG_OK;
 }
@@ -712,7 +713,9 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
       if (E == 128) PBG_TRY(make_tmap(c, &t.tm_q, t.qn, rows_pad, E, 128));
     }
     { LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_prepare_kernel<<<std::min<long long>(c->num_sms * 8, (rows_pad + 7) / 8), 256, 0, s>>>(q, rows, rows_pad, E, t.qn, t.inv_q); }
+      const unsigned pg = static_cast<unsigned>(std::min<long long>(c->num_sms * 8, (rows_pad + 7) / 8));
+      if (E <= 128) topk_prepare_kernel<8, 1><<<pg, 256, 0, s>>>(q, rows, rows_pad, E, t.qn, t.inv_q);
+      else topk_prepare_kernel<2, 4><<<pg, 256, 0, s>>>(q, rows, rows_pad, E, t.qn, t.inv_q); }
     PBG_CUDA(c, cudaGetLastError());
     long long* oi = reinterpret_cast<long long*>(out_idx) + off * k;
     float* os = out_scores + off * k;

@@ -69,29 +69,70 @@ static_assert(TkSmem::kTotal <= 232448, "topk: shared memory budget");
 
 // ------------------------------------------------------------------------------------------------ 1. prepare
 // One warp per row: inv = 1 / max(||x||, 1e-12) (F.normalize's eps), bf16(x * inv) into a [rows_pad, E] matrix whose
-// padding rows are zero.
+// padding rows are zero.  HBM-bound (E fp32 in, E bf16 + 4 B out per row): a warp takes R rows per iteration, every
+// load of those rows in flight before the first reduction (bytes in flight per SM, not instruction count, set the rate),
+// and keeps the values in registers for the scaling pass.  <R = 8, V = 1>: E <= 128; <R = 2, V = 4>: E <= 512 in
+// registers, wider rows are read a second time.
+template <int R, int V>
 __global__ void __launch_bounds__(256) topk_prepare_kernel(const float* __restrict__ x, long long rows, long long rows_pad, int E,
                                                            __nv_bfloat16* __restrict__ xn, float* __restrict__ inv) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long r = warp0; r < rows_pad; r += nwarp) {
-    if (r >= rows) {
-      for (int c = lane * 4; c < E; c += 128) store4<__nv_bfloat16>(xn + r * E + c, make_float4(0.f, 0.f, 0.f, 0.f));
-      continue;
-    }
-    float ss = 0.f;
-    for (int c = lane * 4; c < E; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(x + r * E + c);
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  const bool in_regs = E <= 128 * V;
+  for (long long r0 = warp0 * R; r0 < rows_pad; r0 += nwarp * R) {
+    float4 v[R][V];
+    float ss[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      ss[i] = 0.f;
+      const long long r = r0 + i;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const int c = lane * 4 + j * 128;
+        v[i][j] = (r < rows && c < E && in_regs) ? *reinterpret_cast<const float4*>(x + r * E + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float iv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    if (lane == 0) inv[r] = iv;
-    for (int c = lane * 4; c < E; c += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(x + r * E + c);
-      store4<__nv_bfloat16>(xn + r * E + c, make_float4(v.x * iv, v.y * iv, v.z * iv, v.w * iv));
+    for (int i = 0; i < R; ++i) {
+      const long long r = r0 + i;
+      if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) ss[i] += v[i][j].x * v[i][j].x + v[i][j].y * v[i][j].y + v[i][j].z * v[i][j].z + v[i][j].w * v[i][j].w;
+      } else if (r < rows) {
+        for (int c = lane * 4; c < E; c += 128) {
+          const float4 w = *reinterpret_cast<const float4*>(x + r * E + c);
+          ss[i] += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = r0 + i;
+      if (r >= rows_pad) continue;
+      if (r >= rows) {
+        for (int c = lane * 4; c < E; c += 128) store4<__nv_bfloat16>(xn + r * E + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        continue;
+      }
+      const float iv = 1.f / fmaxf(sqrtf(ss[i]), 1e-12f);
+      if (lane == 0) inv[r] = iv;
+      if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const int c = lane * 4 + j * 128;
+          if (c < E) store4<__nv_bfloat16>(xn + r * E + c, make_float4(v[i][j].x * iv, v[i][j].y * iv, v[i][j].z * iv, v[i][j].w * iv));
+        }
+      } else {
+        for (int c = lane * 4; c < E; c += 128) {
+          const float4 w = *reinterpret_cast<const float4*>(x + r * E + c);
+          store4<__nv_bfloat16>(xn + r * E + c, make_float4(w.x * iv, w.y * iv, w.z * iv, w.w * iv));
+        }
+      }
     }
   }
 }
