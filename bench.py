@@ -381,6 +381,25 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
                     if exchange == "nccl":  # reassemble the outputs on every rank (north_star: NVLink all-gather)
                         dist.all_gather_into_tensor(out["assembled"], out["block"], group=lane_pg[l])
             return
+        if args.stage_ahead == 2:
+            # in-kernel stage-ahead: pass j gathers request j + 1 into the other slot with its idle epilogue warps
+            with torch.cuda.stream(cs):
+                trip0, z0, _ = pool[entries[0]]
+                eng.stage_triplets(0, node_emb, rel_w, trip0, z0)
+                for j, e in enumerate(entries):
+                    out = pool[e][2]
+                    if exchange == "p2p":
+                        eng.set_result_mirrors(**mirrors[e])
+                    if exchange == "mc":
+                        eng.set_result_multicast(**mcasts[e])
+                    nxt = None
+                    if j + 1 < len(entries):
+                        tn, zn, _ = pool[entries[j + 1]]
+                        nxt = (node_emb, rel_w, tn, zn)
+                    eng.score_staged(j & 1, out=out, stage_next=nxt, **kw)
+                    if exchange == "nccl":
+                        dist.all_gather_into_tensor(out["assembled"], out["block"], group=lane_pg[l])
+            return
         # stage-ahead: request j + 1 is gathered on the ingest stream while request j's pass runs; two slots.
         # Everything before this call on the lane is ordered by the compute stream (the ingest stream forks from it).
         fork = torch.cuda.Event(); fork.record(cs); ins.wait_event(fork)
@@ -658,7 +677,7 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
                        "l2": f"inputs rotate over {P} distinct pre-staged batches ({P * per_batch / 2**20:.0f} MiB "
                              f"> 126 MiB L2); no flush", "cuda_graphs": bool(use_graphs),
                        "lanes": S, "ctas_per_pass": [w if w > 0 else num_sms for w in widths[:min(S, 3)]],
-                       "stage_ahead": stage_ahead,
+                       "stage_ahead": int(args.stage_ahead),
                        "collective": {"none": "none", "p2p": "none: every pass writes its result rows into all peers' symmetric-memory "
                                       "windows from its epilogues (NVLink stores, one per peer)",
                                       "mc": "none: every pass writes its result rows once, with multimem.st to the NVSwitch multicast "
@@ -685,8 +704,9 @@ def main() -> None:
     ap.add_argument("--per-gpu-batch", "--batch", dest="batch", type=int, default=0, help="triplets per GPU per step (0: the config's)")
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=6, help="independent requests in flight (one ctx + compute/ingest stream each)")
-    ap.add_argument("--stage-ahead", type=int, default=0, help="1: the next request of a lane is staged (pbg_stage_triplets) on an "
-                    "ingest stream while the current pass runs; 0 (default, measured 3 %% faster in steady state): gather inside the pass")
+    ap.add_argument("--stage-ahead", type=int, default=0, help="0: gather inside the pass (pbg_score_triplets); 1: the next request of a "
+                    "lane is staged (pbg_stage_triplets) on an ingest stream while the current pass runs; 2: the current pass itself "
+                    "gathers the next request with its idle warps (pbg_score_staged_stage_next)")
     ap.add_argument("--exchange", choices=["mc", "p2p", "nccl"], default="mc", help="N > 1: how the outputs are re-assembled")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads of the e2e leg (0: one per lane)")
     ap.add_argument("--e2e-min-s", type=float, default=0.4, help="the e2e leg runs at least this long (and >= --steps calls)")

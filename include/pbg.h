@@ -160,6 +160,16 @@ int pbg_stage_triplets(pbg_ctx* ctx, int slot, const float* node_emb, int64_t N,
                        const int64_t* triplets, const float* z, int64_t B, int want_gen, int want_disc, void* stream);
 int pbg_score_staged(pbg_ctx* ctx, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits,
                      float* probs, void* stream);
+/* pbg_score_staged for `slot` AND the staging of the next request into the other slot in ONE launch: the pass kernel's
+ * epilogue warps gather the next request's rows in 4-row groups whenever they would otherwise wait for an item or an
+ * accumulator, and drain what is left before they exit -- no second kernel, no second stream, nothing in the pass
+ * waits for the gather.  The next request is staged with the operands of the models this call runs; its triplets (and
+ * the table) must stay valid until IT has been scored (its cosine epilogue reads the tail rows through them).  A lane
+ * of requests: pbg_stage_triplets(slot 0, first) once, then pbg_score_staged_stage_next(slot j & 1, ..., request j + 1)
+ * per request and pbg_score_staged for the last. */
+int pbg_score_staged_stage_next(pbg_ctx* ctx, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits,
+                                float* probs, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
+                                const int64_t* next_triplets, const float* next_z, int64_t next_B, void* stream);
 
 /* Index semantics = the reference's: head / tail ids index `node_emb` as a tensor, so -N..-1 count from the end
  * (pro_b_gan_infer.py:139, :186, :188); relation ids go through nn.Embedding, which rejects negatives (:187).

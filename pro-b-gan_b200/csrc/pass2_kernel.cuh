@@ -97,6 +97,8 @@ struct alignas(64) Pass2Params {
   unsigned layer_mask;
   int gather_defer;      // 1: a gather group's completion wait + arrival ride behind the next group's loads
   int gather_external;   // 1: xg0 / xd0 were written by a gather kernel before this launch (phase0_groups = 0)
+  int gather_ahead;      // 1: the gather groups belong to the NEXT request (another staging slot): nothing in this pass waits
+                         //    for them, no arrivals; the warps gather only when idle and drain the rest before they exit
   int no_deps;           // 1: single-layer launch (pbg_linear_bf16): the A operand is the caller's, nothing to wait for
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
@@ -576,7 +578,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     int pend_rb = -1;   // FASTG: row block of the group whose bulk stores are committed but not yet waited for
     auto gather_flush = [&]() {
       if (pend_rb >= 0) {
-        if (lane == 0) { tma_store_wait<0>(); red_relaxed_gpu_add(p.ready + DEP_X * p.rb_cap + pend_rb, 1); }
+        if (lane == 0) { tma_store_wait<0>(); if (!p.gather_ahead) red_relaxed_gpu_add(p.ready + DEP_X * p.rb_cap + pend_rb, 1); }
         __syncwarp();
         pend_rb = -1;
       }
@@ -595,11 +597,14 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       } else {
         pass_gather_group<2>(p.gather, g, lane);
         if (tr && threadIdx.x == kTraceThread) tr[250] = clock64();
-        p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
+        if (!p.gather_ahead) p2_arrive(p, DEP_X, g / kP2GroupsPerBlock, lane, false);
+        else __syncwarp();
       }
     };
-    gather_one();   // everybody starts with one group: nothing else can be ready yet
-    gather_flush(); // ... and the first tiles wait for exactly these groups: no deferral for the first round
+    if (!p.gather_ahead) {
+      gather_one();   // everybody starts with one group: nothing else can be ready yet
+      gather_flush(); // ... and the first tiles wait for exactly these groups: no deferral for the first round
+    }
     bool bias_ok = !BIASS;
     long long pf_wait = 0, pf_total = 0, pf_n = 0;
     // generator output rows of the previous PEPI_TANH tile may still be leaving through the quarter's two staging tiles
@@ -1048,6 +1053,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (tr && lane == 0) busy += clock64() - t_busy0;
       if (ti) ti[3] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.gather_ahead) {   // whatever is left of the next request's rows (claimed from the same counter by every warp)
+      pair_settle();
+      while (more_groups) gather_one();
+      gather_flush();
     }
     // every lane: its bulk stores must have READ the staging tile before the CTA (and its shared memory) goes away; their
     // global / peer writes complete with the grid -- waiting for them here would put an NVLink round trip on every CTA's exit

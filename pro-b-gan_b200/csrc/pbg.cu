@@ -90,6 +90,8 @@ struct StageSlot {
   CUtensorMap tm_xg0, tm_xd0;
   long long B = -1;     // rows of the staged request (-1: nothing staged)
   bool has_g = false, has_d = false;
+  bool has_xt = false;  // xt holds the tail rows (staging kernel); otherwise the cosine epilogue indexes the table itself
+  const float* node_emb = nullptr; long long N = 0; const long long* tails = nullptr;   // ... through these (stride 3)
 };
 
 thread_local std::string g_create_error;
@@ -321,7 +323,7 @@ int pass_grid(const pbg_ctx* c) {
 
 struct Pass;
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot = nullptr);
+                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot = nullptr, bool gather_ahead = false);
 
 struct Pass {
   const float* node_emb = nullptr; long long N = 0;
@@ -424,7 +426,7 @@ cudaError_t launch_p2(pbg_ctx* c, const Pass2Params& p, int grid, cudaStream_t s
 
 // The pair kernel (pass2_kernel.cuh): 256-row blocks, tiles of 256 x {256 | 128}, one CTA pair per tile.
 int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp, long long off, long long rows,
-                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot) {
+                 void* gen_out, float* scores, bool external_gather, const StageSlot* slot, bool gather_ahead) {
   const int grid = pass_grid(c) & ~1;  // whole pairs
   Pass2Params p;
   memset(&p, 0, sizeof p);
@@ -469,6 +471,10 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   // ticket, layer by layer (a topological order); the scheduler thread polls a ticket's dependency counter.
   p.phase0_groups = external_gather ? 0 : nrb * kP2GroupsPerBlock;
   p.gather_external = external_gather ? 1 : 0;
+  if (gather_ahead) {   // gp describes the NEXT request, gathered into the other staging slot while this pass runs
+    p.phase0_groups = static_cast<int>((gp.B + 3) / 4);
+    p.gather_ahead = 1;
+  }
   {
     // Waves: the row blocks can be cut into `waves` groups whose layer phases are interleaved (L0 of every wave,
     // then L1 of every wave, then L2).  One wave measured best at every size (PBG_WAVES to experiment).
@@ -511,8 +517,10 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
-  if (scores && slot) {   // the staging kernel left the tail rows, in request order, in the slot: no index, no table
+  if (scores && slot && slot->has_xt) {   // the staging kernel left the tail rows, in request order, in the slot
     p.cosine = scores; p.tail_tab = slot->xt; p.n_ent = slot->cap; p.tail_idx = nullptr; p.tail_stride = 0;
+  } else if (scores && slot) {             // staged by the previous pass: the tail rows are read through the request's ids
+    p.cosine = scores; p.tail_tab = slot->node_emb; p.n_ent = slot->N; p.tail_idx = slot->tails; p.tail_stride = 3;
   } else if (scores) {
     p.cosine = scores; p.tail_tab = a.node_emb; p.n_ent = a.N;
     p.tail_idx = a.tails + off * a.ts; p.tail_stride = a.ts;
@@ -1039,7 +1047,8 @@ int pbg_stage_triplets(pbg_ctx* c, int slot, const float* node_emb, int64_t N, c
   { LaunchScope ls(c, PBG_K_GATHER, s);
     stage_rows_kernel<<<blocks, 128, 0, s>>>(sp); }
   PBG_CUDA(c, cudaGetLastError());
-  st.B = B; st.has_g = want_gen != 0; st.has_d = want_disc != 0;
+  st.B = B; st.has_g = want_gen != 0; st.has_d = want_disc != 0; st.has_xt = want_gen != 0;
+  st.node_emb = node_emb; st.N = N; st.tails = t + 2;
   return PBG_OK;
 }
 
@@ -1060,6 +1069,42 @@ int pbg_score_staged(pbg_ctx* c, int slot, void* gen_out, int out_dtype, float* 
   PBG_TRY(ensure_ws(c, PBG_PREC_BF16, st.B, a.stream));
   GatherParams gp{};
   return launch_pass2(c, c->ws_bf16, a, gp, 0, st.B, gen_out, gen_scores, true, &st);
+}
+
+int pbg_score_staged_stage_next(pbg_ctx* c, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits, float* probs,
+                                const float* node_emb, int64_t N, const float* rel_emb, int64_t R, const int64_t* next_triplets,
+                                const float* next_z, int64_t next_B, void* stream) {
+  if (!c) return PBG_ERR_INVALID;
+  if (slot < 0 || slot > 1) return fail(c, PBG_ERR_INVALID, "score_staged: slot must be 0 or 1");
+  StageSlot& st = c->stage[slot];
+  StageSlot& nx = c->stage[1 - slot];
+  if (st.B <= 0) return fail(c, PBG_ERR_INVALID, "score_staged: nothing staged in slot %d", slot);
+  if (next_B <= 0 || next_B > kMaxChunk) return fail(c, PBG_ERR_INVALID, "stage next: B must be in [1, %lld]", kMaxChunk);
+  if (!node_emb || !rel_emb || !next_triplets) return fail(c, PBG_ERR_INVALID, "null tensor");
+  Pass a;
+  a.gen_out = gen_out; a.out_dtype = out_dtype; a.gen_scores = gen_scores; a.logits = logits; a.probs = probs;
+  a.run_g = (gen_out != nullptr || gen_scores != nullptr); a.run_d = (logits != nullptr);
+  if (a.run_g && !st.has_g) return fail(c, PBG_ERR_INVALID, "score_staged: slot %d holds no generator operands", slot);
+  if (a.run_d && !st.has_d) return fail(c, PBG_ERR_INVALID, "score_staged: slot %d holds no discriminator operands", slot);
+  if (!a.run_g && !a.run_d) return fail(c, PBG_ERR_INVALID, "score_staged_stage_next: no result requested");
+  if (a.run_g && !next_z) return fail(c, PBG_ERR_INVALID, "generator needs latents z");
+  a.B = st.B; a.prec = PBG_PREC_BF16; a.stream = (cudaStream_t)stream;
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  PBG_TRY(ensure_ws(c, PBG_PREC_BF16, st.B, a.stream));
+  PBG_TRY(ensure_stage(c, nx, next_B, a.stream));
+  // the next request gets the operands this pass produces results for (same models in flight)
+  const long long* t = reinterpret_cast<const long long*>(next_triplets);
+  GatherParams gp{};
+  gp.node_emb = node_emb; gp.rel_emb = rel_emb; gp.N = N; gp.R = R; gp.E = c->dims.embed_dim; gp.Z = c->dims.noise_dim;
+  gp.heads = t; gp.rels = t + 1; gp.tails = t + 2; gp.head_stride = gp.rel_stride = gp.tail_stride = 3;
+  gp.z = next_z;
+  gp.xg = a.run_g ? nx.xg0 : nullptr; gp.ldg = c->kg0p;
+  gp.xd = a.run_d ? nx.xd0 : nullptr; gp.ldd = c->kd0p;
+  gp.B = next_B; gp.err_flag = c->err_flag;
+  PBG_TRY(launch_pass2(c, c->ws_bf16, a, gp, 0, st.B, gen_out, gen_scores, true, &st, true));
+  nx.B = next_B; nx.has_g = a.run_g; nx.has_d = a.run_d; nx.has_xt = false;
+  nx.node_emb = node_emb; nx.N = N; nx.tails = t + 2;
+  return PBG_OK;
 }
 
 int pbg_linear_bf16(pbg_ctx* c, int model, int layer, const void* a, void* out, int64_t M, void* stream) {

@@ -23,7 +23,7 @@ SYMBOLS = (
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
     "pbg_set_launch_width", "pbg_set_result_mirrors", "pbg_topk_prepare", "pbg_topk", "pbg_parse_index_rows", "pbg_format_f32_json", "pbg_format_i64_json",
-    "pbg_reserve", "pbg_stage_triplets", "pbg_score_staged", "pbg_set_result_multicast", "pbg_topk_last_flagged", "pbg_score_triplets_host_packed",
+    "pbg_reserve", "pbg_stage_triplets", "pbg_score_staged", "pbg_set_result_multicast", "pbg_topk_last_flagged", "pbg_score_triplets_host_packed", "pbg_score_staged_stage_next",
 )
 
 
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
         "pbg_set_result_multicast": (C.c_int, [vp, vp, vp, vp, vp]),
         "pbg_topk_last_flagged": (i64, [vp, vp]),
         "pbg_score_triplets_host_packed": (C.c_int, [vp, vp, i64, vp, i64, vp, vp, i64, i32]),
+        "pbg_score_staged_stage_next": (C.c_int, [vp, i32, vp, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -337,9 +337,11 @@ class Engine:
         return B
 
     def score_staged(self, slot: int, want_gen_out=False, want_gen_scores=False, want_disc=True,
-                     out_dtype=torch.float32, out: dict | None = None):
+                     out_dtype=torch.float32, out: dict | None = None, stage_next: tuple | None = None):
         """The G + D pass over a staged request on the CURRENT stream (the compute stream); the caller has ordered it
-        after the slot's stage_triplets.  Same result dict as score_triplets (bf16 mode)."""
+        after the slot's stage_triplets.  Same result dict as score_triplets (bf16 mode).
+        ``stage_next = (node_emb, rel_w, triplets, z)``: the same launch also stages that request into the other slot
+        (pbg_score_staged_stage_next) -- its tensors must stay alive until it has been scored."""
         res, out = {}, (out or {})
         B = getattr(self, "_staged_rows", {}).get(int(slot))
         if B is None:
@@ -359,10 +361,30 @@ class Engine:
         scores = buf("gen_scores", want_gen_scores, (B,), torch.float32)
         logits = buf("logits", want_disc, (B,), torch.float32)
         probs = buf("probs", want_disc, (B,), torch.float32)
+        dt = cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32
         with torch.cuda.device(self.device):
-            cabi.check(self._lib.pbg_score_staged(
-                self._h, int(slot), _ptr(gen_out), cabi.DT_BF16 if out_dtype == torch.bfloat16 else cabi.DT_F32,
-                _ptr(scores), _ptr(logits), _ptr(probs), self._stream()), self._h)
+            if stage_next is None:
+                cabi.check(self._lib.pbg_score_staged(self._h, int(slot), _ptr(gen_out), dt, _ptr(scores), _ptr(logits),
+                                                      _ptr(probs), self._stream()), self._h)
+            else:
+                n_emb, n_rel, n_trip, n_z = stage_next
+                n_emb, n_rel = self._f32(n_emb, self.E, "node_emb"), self._f32(n_rel, self.E, "rel_emb.weight")
+                n_trip = self._i64(n_trip, "triplets")
+                if n_trip.dim() != 2 or n_trip.shape[1] != 3 or not n_trip.is_contiguous():
+                    raise ValueError("the next request's triplets must be a contiguous [B, 3] tensor")
+                run_g = want_gen_out or want_gen_scores
+                if run_g:
+                    if n_z is None:
+                        raise ValueError("generator pass needs latents z")
+                    n_z = self._f32(n_z, self.Z, "z")
+                cabi.check(self._lib.pbg_score_staged_stage_next(
+                    self._h, int(slot), _ptr(gen_out), dt, _ptr(scores), _ptr(logits), _ptr(probs), _ptr(n_emb), n_emb.shape[0],
+                    _ptr(n_rel), n_rel.shape[0], _ptr(n_trip), _ptr(n_z if run_g else None), n_trip.shape[0], self._stream()),
+                    self._h)
+                self._staged_rows[1 - int(slot)] = n_trip.shape[0]
+                if not hasattr(self, "_staged_keep"):
+                    self._staged_keep = {}
+                self._staged_keep[1 - int(slot)] = (n_emb, n_rel, n_trip, n_z)   # alive until that slot is staged again
         if want_gen_out:
             res["gen_out"] = gen_out
         if want_gen_scores:

@@ -471,6 +471,57 @@ def test_staged_pipeline_in_a_cuda_graph_with_two_slots(cuda_models, dev_tables,
     eng.check_indices()
 
 
+def test_pass_that_stages_the_next_request_equals_the_fused_pass(cuda_models, dev_tables, synth, dev):
+    """pbg_score_staged_stage_next: pass j gathers request j + 1 into the other slot with its idle epilogue warps (same
+    gather code as the fused pass, no arrivals, drained before exit).  A chain of ragged requests, bit for bit against
+    the fused pass, eagerly and as one CUDA graph."""
+    import modular_prot_b_gan as m
+    sizes = [1000, 4096, 31, 257, 5000, 256, 3]
+    eng = m.make_fused_engine(*cuda_models, ctas=48)
+    inputs = [(synth.make_triplets(B, seed=700 + i).to(dev), synth.make_latents(B, seed=800 + i).to(dev)) for i, B in enumerate(sizes)]
+    ref = [{k: v.clone() for k, v in _pass(eng, dev_tables, t, z).items()} for t, z in inputs]
+    eng.reserve(max(sizes), "bf16", 2)
+    kw = dict(want_gen_out=True, want_gen_scores=True, want_disc=True, out_dtype=torch.bfloat16)
+
+    def chain(outs=None):
+        res = []
+        eng.stage_triplets(0, *dev_tables, *inputs[0])
+        for j in range(len(inputs)):
+            nxt = (*dev_tables, *inputs[j + 1]) if j + 1 < len(inputs) else None
+            res.append(eng.score_staged(j & 1, stage_next=nxt, out=None if outs is None else outs[j], **kw))
+        return res
+
+    got = chain()
+    torch.cuda.synchronize()
+    eng.check_indices()
+    for j in range(len(inputs)):
+        for k in ref[j]:
+            assert torch.equal(got[j][k], ref[j][k]), f"request {j} (B = {sizes[j]}): {k} differs"
+    outs = [{k: torch.zeros_like(v) for k, v in r.items()} for r in ref]
+    cs = torch.cuda.Stream(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(cs):
+        with torch.cuda.graph(g, stream=cs):
+            chain(outs)
+    for _ in range(2):
+        for o in outs:
+            for v in o.values():
+                v.zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(cs):
+            g.replay()
+        torch.cuda.synchronize()
+        for j in range(len(inputs)):
+            for k in ref[j]:
+                assert torch.equal(outs[j][k], ref[j][k]), f"graph, request {j}: {k} differs"
+    # a bad id in the NEXT request is flagged by the pass that stages it
+    bad = inputs[1][0].clone(); bad[3, 0] = 70000
+    eng.stage_triplets(0, *dev_tables, *inputs[0])
+    eng.score_staged(0, stage_next=(*dev_tables, bad, inputs[1][1]), **kw)
+    with pytest.raises(IndexError):
+        eng.check_indices()
+
+
 def test_staged_request_flags_bad_ids_and_misuse(engine, dev_tables, synth, dev):
     B = 64
     z = synth.make_latents(B).to(dev)
