@@ -222,6 +222,15 @@ int pbg_debug_trace(pbg_ctx* ctx, int enable, int64_t* host_out, int64_t n_slots
  * (bench.py does exactly that).  One pass alone is fastest at full width. */
 int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
 
+/* Workspace discard (default on; the environment variable PBG_DISCARD=0 turns it off for new contexts).  The layers of
+ * a bf16-mode pass hand their activations to each other through L2 in workspace buffers of the ctx.  Once the
+ * consuming layer has finished with a 256-row block those lines are dead but dirty, and when several contexts'
+ * workspaces cycle through the L2 they are written back to HBM on eviction (32 MB per 4096-triplet pass that nothing
+ * reads).  With the option on the pass kernel drops each dead block from L2 (`discard.global.L2`) instead.  Results
+ * do not depend on the setting.  No reference counterpart: torch leaves its intermediates to the cache
+ * (pro_b_gan_infer.py:201, :207). */
+int pbg_set_workspace_discard(pbg_ctx* ctx, int on);
+
 /* Result mirrors -- the output exchange of a batch-sharded multi-GPU job without a collective.  After this call every
  * bf16-mode pass of the ctx writes each result row not only to the caller's own gen_out / gen_scores / logits /
  * probs but also, at the same row index, to the n (<= 7) mirror buffers given here: device pointers into peer GPUs'

@@ -100,6 +100,8 @@ struct alignas(64) Pass2Params {
   int gather_ahead;      // 1: the gather groups belong to the NEXT request (another staging slot): nothing in this pass waits
                          //    for them, no arrivals; the warps gather only when idle and drain the rest before they exit
   int no_deps;           // 1: single-layer launch (pbg_linear_bf16): the A operand is the caller's, nothing to wait for
+  int discard;           // 1: dead workspace row blocks (activations and gathered rows the next layer has consumed) are
+                         //    dropped from L2 with discard.global.L2 instead of being written back to HBM when evicted
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
   int n_total;          // tickets of this launch
@@ -224,6 +226,16 @@ __device__ __forceinline__ void p2_poll_dep(const Pass2Params& p, int dep_kind, 
 #endif
   }
   fence_proxy_async_all();
+}
+
+// Workspace lines that nothing will read again (a row block of activations whose consumer layer has finished with it)
+// are dirty in L2, and with several lanes' workspaces cycling through the cache they would be written back to HBM on
+// eviction: tens of megabytes per pass that no one ever reads.  discard.global.L2 drops a 128-byte line without the
+// write-back (SASS: CCTL.E.RML2).  Warp `part` of `nparts` takes every nparts-th 4 KB piece of [base, base + bytes).
+__device__ __forceinline__ void p2_discard(const void* base, size_t bytes, int part, int nparts, int lane) {
+  const char* b = static_cast<const char*>(base);
+  for (size_t off = static_cast<size_t>(part) * 4096 + static_cast<size_t>(lane) * 128; off < bytes; off += static_cast<size_t>(nparts) * 4096)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(b + off) : "memory");
 }
 
 // Tail-embedding values of 32 columns for this warp's 32 rows: coalesced 16-byte loads (four rows per instruction),
@@ -569,6 +581,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
+    const bool own_gather = p.phase0_groups > 0 && !p.gather_ahead && !p.gather_external;  // xg0 / xd0 were gathered by this launch, for this launch
     // The gather: 4-row groups claimed from a counter (claimed, not statically assigned: like the tickets, nothing may
     // depend on CTAs of this launch that are not resident yet -- several launches may share the device, and whatever
     // subset of a launch's CTAs is running has to be able to finish the pass on its own).  A warp gathers whenever it
@@ -758,6 +771,11 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           p2_arrive(p, ly.out_kind, rb, lane, true, (tr && threadIdx.x == kTraceThread) ? &pf_wait : nullptr);
           if (tr && threadIdx.x == kTraceThread) { pf_total += clock64() - t0; pf_n += 1; }
         }
+        // G layer 1, first tile of the row block: every G L0 tile of the block has been published, so the block's gathered
+        // rows (written by this launch's gather) are dead
+        if (p.discard && kind == IT_G_L1 && n_blk == 0 && own_gather && p.gather.xg != nullptr)
+          p2_discard(static_cast<const char*>(p.gather.xg) + static_cast<size_t>(rb) * kP2Rows * p.gather.ldg * 2,
+                     static_cast<size_t>(kP2Rows) * p.gather.ldg * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block
@@ -791,10 +809,19 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
+        // first tile of the row block: every D L0 tile of the block has been published -> its gathered rows are dead
+        if (p.discard && n_blk == 0 && own_gather && p.gather.xd != nullptr)
+          p2_discard(static_cast<const char*>(p.gather.xd) + static_cast<size_t>(rb) * kP2Rows * p.gather.ldd * 2,
+                     static_cast<size_t>(kP2Rows) * p.gather.ldd * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
         const int old = warp_publish_fetch(p.fin + FIN_D * p.rb_cap + rb, lane);
         if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
           fence_acq_rel_gpu();
           __syncwarp();
+          // every D L1 tile of the block is done (its MMAs completed before its warps arrived here): the block's D L0
+          // activations are dead
+          if (p.discard)
+            p2_discard(reinterpret_cast<const char*>(p.layer[IT_D_L0].out) + static_cast<size_t>(rb) * kP2Rows * p.layer[IT_D_L0].ldo * 2,
+                       static_cast<size_t>(kP2Rows) * p.layer[IT_D_L0].ldo * 2, 0, 1, lane);
           // 8 rows per lane; all loads of a row group in flight together, summed in slot order
           float s[kP2Rows / 32];
 #pragma unroll
@@ -1025,6 +1052,15 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
+        }
+        // this tile's MMAs have read the block's G L1 activations, and every G L1 tile of the block was published before
+        // this tile was (each after its own MMAs): with one G L2 tile per row block both activation blocks are dead
+        if (p.discard && ly.n_tiles == 1) {
+          const int part = static_cast<int>(rank) * kP2Epi + wep;
+          p2_discard(reinterpret_cast<const char*>(p.layer[IT_G_L0].out) + static_cast<size_t>(rb) * kP2Rows * p.layer[IT_G_L0].ldo * 2,
+                     static_cast<size_t>(kP2Rows) * p.layer[IT_G_L0].ldo * 2, part, kP2WarpsPerPair, lane);
+          p2_discard(reinterpret_cast<const char*>(p.layer[IT_G_L1].out) + static_cast<size_t>(rb) * kP2Rows * p.layer[IT_G_L1].ldo * 2,
+                     static_cast<size_t>(kP2Rows) * p.layer[IT_G_L1].ldo * 2, part, kP2WarpsPerPair, lane);
         }
         if (tpt) tr[236] = clock64();
         if (want_cos && !in_cta) {

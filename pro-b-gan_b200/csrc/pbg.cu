@@ -126,6 +126,7 @@ struct pbg_ctx {
   TopkState tk;
   long long launches = 0;
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
+  int discard = 1;      // pbg_set_workspace_discard (PBG_DISCARD sets the initial value)
   int n_mirror = 0;     // pbg_set_result_mirrors
   void* mir_gen[kMaxMirrors] = {}; float* mir_cos[kMaxMirrors] = {}; float* mir_logits[kMaxMirrors] = {}; float* mir_probs[kMaxMirrors] = {};
   void* mc_gen = nullptr; float *mc_cos = nullptr, *mc_logits = nullptr, *mc_probs = nullptr;   // pbg_set_result_multicast
@@ -514,6 +515,10 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   p.poll_ns = poll_env;
   static const int defer_env = [] { const char* e = getenv("PBG_GATHER_DEFER"); return e ? atoi(e) : 1; }();
   p.gather_defer = defer_env;
+  // dead workspace row blocks are dropped from L2 instead of being written back to HBM (pass2_kernel.cuh: p2_discard;
+  // in rotation over six lanes' workspaces: 31.9 -> 1.9 MB of DRAM writes per 4096-triplet launch,
+  // profiles/dram_steady_r2.txt)
+  p.discard = c->discard;
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
@@ -840,6 +845,12 @@ int pbg_set_launch_width(pbg_ctx* c, int n_ctas) {
   return PBG_OK;
 }
 
+int pbg_set_workspace_discard(pbg_ctx* c, int on) {
+  if (!c) return PBG_ERR_INVALID;
+  c->discard = on ? 1 : 0;
+  return PBG_OK;
+}
+
 int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
   if (!out || !dims) return fail(nullptr, PBG_ERR_INVALID, "null argument");
   *out = nullptr;
@@ -865,6 +876,7 @@ int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
   if (!c) return fail(nullptr, PBG_ERR_NOMEM, "out of host memory");
   c->dims = *dims;
   c->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("PBG_DISCARD")) c->discard = atoi(e) != 0;
   c->kg0 = 2 * E + Z; c->kg0p = round_up(c->kg0, kBlockK);
   c->kd0 = 3 * E;     c->kd0p = round_up(c->kd0, kBlockK);
   c->hgp = round_up(HG, 128); c->hdp = round_up(HD, 128);

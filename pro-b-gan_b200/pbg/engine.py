@@ -75,6 +75,10 @@ class Engine:
         """CTAs (SMs) one fused pass occupies; 0 = the whole device.  See include/pbg.h."""
         cabi.check(self._lib.pbg_set_launch_width(self._h, int(ctas)), self._h)
 
+    def set_workspace_discard(self, on: bool) -> None:
+        """Dead activation row blocks are dropped from L2 instead of being written back to HBM (default on).  See include/pbg.h."""
+        cabi.check(self._lib.pbg_set_workspace_discard(self._h, int(bool(on))), self._h)
+
     def cosine_topk(self, queries: torch.Tensor, table: torch.Tensor, k: int):
         """``F.normalize(queries) @ F.normalize(table).T`` followed by ``.topk(k, dim=1)`` without the [B, N] matrix
         (pro_b_gan_infer.py:146-151, :231-236).  Returns (scores fp32 [B, k], indices int64 [B, k]) like torch.topk.

@@ -334,6 +334,30 @@ def test_launch_width_does_not_change_a_single_bit(cuda_models, engine, dev_tabl
             assert torch.equal(res[k], ref[k]), f"width {ctas}: {k} differs"
 
 
+@pytest.mark.parametrize("B", [31, 300, 4096, 9000])
+def test_workspace_discard_does_not_change_a_single_bit(cuda_models, dev_tables, synth, dev, B):
+    """pbg_set_workspace_discard: dropping dead activation / gathered row blocks from L2 (discard.global.L2) inside the pass
+    changes no result -- same engine run repeatedly (a pass writes over what the previous one discarded), generator-only
+    and discriminator-only passes, and a second engine with the option off as the reference."""
+    import modular_prot_b_gan as m
+    off, on = m.make_fused_engine(*cuda_models), m.make_fused_engine(*cuda_models)
+    off.set_workspace_discard(False)
+    on.set_workspace_discard(True)
+    for rep in range(3):
+        trip, z = synth.make_triplets(B, seed=700 + rep).to(dev), synth.make_latents(B, seed=800 + rep).to(dev)
+        ref = {k: v.clone() for k, v in _pass(off, dev_tables, trip, z).items()}
+        res = {k: v.clone() for k, v in _pass(on, dev_tables, trip, z).items()}
+        for k in ref:
+            assert torch.equal(res[k], ref[k]), f"rep {rep}: {k} differs with the discards on"
+        for kw in (dict(want_gen_out=True, want_gen_scores=True, want_disc=False), dict(want_gen_out=False, want_gen_scores=False, want_disc=True)):
+            a = off.score_triplets(*dev_tables, trip, z, precision="bf16", **kw)
+            b = on.score_triplets(*dev_tables, trip, z, precision="bf16", **kw)
+            for k in a:
+                if a[k] is not None:
+                    assert torch.equal(a[k], b[k]), f"rep {rep} {kw}: {k} differs with the discards on"
+    off.check_indices(); on.check_indices()
+
+
 def test_passes_on_concurrent_lanes_match_sequential(cuda_models, dev_tables, synth, dev):
     """Three ctxs on three streams, 48 SMs each, passes in flight together (bench.py's lanes)."""
     import modular_prot_b_gan as m
