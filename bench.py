@@ -18,8 +18,9 @@ Weak scaling: B triplets per GPU per step, batch-index sharded, outputs re-assem
 Timed region (SURVEY.md 8d "steady state: >= 100 back-to-back forward calls"; VERDICT r1 "next" #1):
   * requests are independent, so they are kept in flight on `--lanes` lanes -- one engine (ctx), one compute stream
     and one ingest stream per lane; lane l's passes occupy about a third of the SMs (50 / 50 / 48) and run beside the
-    other lanes' passes; the NEXT request of a lane is staged (gather + concat + cast, pbg_stage_triplets) on the
-    ingest stream while the current pass runs (pbg_score_staged);
+    other lanes' passes; every pass also gathers (+ concatenates + casts) the lane's NEXT request into the ctx's other
+    staging slot with its idle epilogue warps (pbg_score_staged_stage_next; `--stage-ahead 0`: each pass gathers its
+    own request first, pbg_score_triplets);
   * inputs rotate over a pool of pre-staged batches larger than L2; every pool entry is executed once before timing;
   * each lane's rotation over its pool entries is ONE CUDA graph; the timed region replays the lanes' graphs
     back to back: `steps` x `repeats` passes inside one CUDA-event pair, `repeats` chosen so that the region lasts
@@ -507,10 +508,12 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
         tail_graphs_for(n_timed % P)
     timed(min(n_timed, 2 * P))   # one more untimed run of the exact graph set
 
-    trials = []
+    trials, kernel_mhz = [], []
     with ClockSampler(local_rank, period_s=0.010) as clk:
         for _ in range(max(1, args.trials)):
             trials.append(max_over_ranks(timed(n_timed)))
+            # SM clock during the last pass of every lane in this trial, measured inside the kernel (clock64 / globaltimer)
+            kernel_mhz.append(round(statistics.median(e.last_pass_sm_clock() for e in engines), 1))
     for e in engines:
         e.check_indices()
     ms_med, ms_best = statistics.median(trials), min(trials)
@@ -626,6 +629,7 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     # cap during it (SM clocks below the maximum) the sustained cuBLAS figure is the like-for-like peak, otherwise the
     # burst one.  Both fractions are always printed.
     clock_summary = clk.summary()
+    clock_summary["sm_mhz_in_kernel_by_trial"] = kernel_mhz   # clock64 / globaltimer over a pass's lifetime (pbg_last_pass_sm_clock)
     capped = "sw_power_cap" in (clock_summary.get("reasons") or [])
     use_sustained = capped and ms_med >= 25.0
     peak = peaks["bf16_sustained"] if use_sustained else peaks["bf16_burst"]
@@ -704,9 +708,10 @@ def main() -> None:
     ap.add_argument("--per-gpu-batch", "--batch", dest="batch", type=int, default=0, help="triplets per GPU per step (0: the config's)")
     ap.add_argument("--graphs", type=int, default=1)
     ap.add_argument("--lanes", type=int, default=6, help="independent requests in flight (one ctx + compute/ingest stream each)")
-    ap.add_argument("--stage-ahead", type=int, default=0, help="0: gather inside the pass (pbg_score_triplets); 1: the next request of a "
-                    "lane is staged (pbg_stage_triplets) on an ingest stream while the current pass runs; 2: the current pass itself "
-                    "gathers the next request with its idle warps (pbg_score_staged_stage_next)")
+    ap.add_argument("--stage-ahead", type=int, default=2, help="2 (default): every pass gathers the lane's NEXT request with its idle "
+                    "epilogue warps (pbg_score_staged_stage_next: +6 %% samples per SM clock, +2 %% under the power cap); 0: the pass "
+                    "gathers its own request first (pbg_score_triplets); 1: the next request of a lane is staged by a separate kernel "
+                    "(pbg_stage_triplets) on an ingest stream while the current pass runs")
     ap.add_argument("--exchange", choices=["mc", "p2p", "nccl"], default="mc", help="N > 1: how the outputs are re-assembled")
     ap.add_argument("--e2e-threads", type=int, default=0, help="host threads of the e2e leg (0: one per lane)")
     ap.add_argument("--e2e-min-s", type=float, default=0.4, help="the e2e leg runs at least this long (and >= --steps calls)")

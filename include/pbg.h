@@ -222,6 +222,11 @@ int pbg_debug_trace(pbg_ctx* ctx, int enable, int64_t* host_out, int64_t n_slots
  * (bench.py does exactly that).  One pass alone is fastest at full width. */
 int pbg_set_launch_width(pbg_ctx* ctx, int n_ctas);
 
+/* SM clock (MHz) during the last bf16-mode pass of the ctx, measured inside the kernel: CTA 0 reads clock64() and
+ * %globaltimer when its roles start and when it exits.  Diagnostics for bench.py's `clocks` entry -- NVML's clock
+ * reading is a sample of a much slower loop than a 50 ms timed region.  Synchronises `stream`. */
+int pbg_last_pass_sm_clock(pbg_ctx* ctx, void* stream, double* mhz_out);
+
 /* Workspace discard (default on; the environment variable PBG_DISCARD=0 turns it off for new contexts).  The layers of
  * a bf16-mode pass hand their activations to each other through L2 in workspace buffers of the ctx.  Once the
  * consuming layer has finished with a 256-row block those lines are dead but dirty, and when several contexts'

@@ -444,6 +444,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
   // and the scheduler) has completed.  Everything above touches only this CTA and the immutable weights.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  long long* const clk0 = reinterpret_cast<long long*>(smem + L::kXchgOff + L::kXchgBytes) + 8;   // [2], behind the diagnostics' t_issue[]
+  if (blockIdx.x == 0 && threadIdx.x == 0) { clk0[0] = clock64(); clk0[1] = static_cast<long long>(globaltimer_ns()); }
   long long* const tr = (TR && p.trace) ? p.trace + kTraceSlots * blockIdx.x : nullptr;
   if (tr && threadIdx.x == 0) { tr[0] = clock64(); tr[14] = static_cast<long long>(globaltimer_ns()); tr[254] = t_entry; }
 
@@ -1115,6 +1117,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     tmem_dealloc_pair<512>(tmem_base);
   }
   // the last CTA to finish re-arms the scheduler and zeroes the arrival counters for the next launch
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.sched->clk_ticks = clock64() - clk0[0];
+    p.sched->clk_ns = static_cast<long long>(globaltimer_ns()) - clk0[1];
+  }
   if (threadIdx.x == 0) {
     const int old = atomicAdd(&p.sched->done, 1);
     *last_flag = (old == static_cast<int>(gridDim.x) - 1);

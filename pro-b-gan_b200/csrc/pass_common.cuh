@@ -25,6 +25,10 @@ struct PassSched {
   int p0_next;  // next phase-0 gather group
   int init;     // 0 -> 1 by the CTA that seeds the queue
   int done;     // CTAs that have finished
+  int pad_;
+  // SM clock of the last launch, measured by CTA 0: clock64() ticks and globaltimer nanoseconds between the start of
+  // its roles and its exit (pbg_last_pass_sm_clock; NVML's clock reading is a sample of a slower loop)
+  long long clk_ticks, clk_ns;
 };
 
 

@@ -741,14 +741,17 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
     const int npairs = grid / 2;
     const int n_rb = static_cast<int>(rows_pad / 256);
     const int n_tiles = static_cast<int>(t.n_pad / 256);
-    // work items = query block x tile range, about one round over the pairs
+    // work units = query block x visited tile, query-block major; every pair takes an equal, contiguous span of them
+    // (cut at query-block boundaries inside the kernel), so all SMs scan the same number of tiles whatever B is.  A
+    // query block met by s pairs needs s list slots per row: the span is at least tiles / (kTkMaxRanges - 1).
     auto split = [&](int tiles, TopkParams& p) {
       p.n_rb = n_rb;
       p.n_tiles = tiles;
-      p.n_ranges = std::max(1, std::min({kTkMaxRanges, npairs / n_rb, tiles}));
-      p.tiles_per_range = (tiles + p.n_ranges - 1) / p.n_ranges;
-      p.n_ranges = (tiles + p.tiles_per_range - 1) / p.tiles_per_range;   // no empty range
-      p.n_items = n_rb * p.n_ranges;
+      p.total = n_rb * tiles;
+      p.span = std::max({1, (p.total + npairs - 1) / npairs, (tiles + kTkMaxRanges - 2) / (kTkMaxRanges - 1)});
+      p.n_ranges = 1;
+      for (int rb = 0; rb < n_rb; ++rb)
+        p.n_ranges = std::max(p.n_ranges, ((rb + 1) * tiles - 1) / p.span - (rb * tiles) / p.span + 1);
     };
     TopkParams ps, pm;
     memset(&ps, 0, sizeof ps); memset(&pm, 0, sizeof pm);
@@ -780,13 +783,13 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
       attr_dev = c->dims.device;
     }
     { LaunchScope ls(c, PBG_K_TOPK, s);
-      pbg_topk_scan_kernel<TK_SAMPLE><<<std::min(grid, 2 * ps.n_items), kPassThreads, TkSmem::kTotal, s>>>(ps); }
+      pbg_topk_scan_kernel<TK_SAMPLE><<<std::min(grid, 2 * ((ps.total + ps.span - 1) / ps.span)), kPassThreads, TkSmem::kTotal, s>>>(ps); }
     PBG_CUDA(c, cudaGetLastError());
     { LaunchScope ls(c, PBG_K_OTHER, s);
       topk_tau_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(t.samp_keys, n_slists, rows, rows_pad, k, t.tau); }
     PBG_CUDA(c, cudaGetLastError());
     { LaunchScope ls(c, PBG_K_TOPK, s);
-      pbg_topk_scan_kernel<TK_SCAN><<<std::min(grid, 2 * pm.n_items), kPassThreads, TkSmem::kTotal, s>>>(pm); }
+      pbg_topk_scan_kernel<TK_SCAN><<<std::min(grid, 2 * ((pm.total + pm.span - 1) / pm.span)), kPassThreads, TkSmem::kTotal, s>>>(pm); }
     PBG_CUDA(c, cudaGetLastError());
     { LaunchScope ls(c, PBG_K_OTHER, s);
       topk_rescore_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask,
@@ -842,6 +845,20 @@ int pbg_set_launch_width(pbg_ctx* c, int n_ctas) {
   if (!c) return PBG_ERR_INVALID;
   if (n_ctas < 0) return fail(c, PBG_ERR_INVALID, "launch width must be >= 0");
   c->launch_ctas = n_ctas;
+  return PBG_OK;
+}
+
+int pbg_last_pass_sm_clock(pbg_ctx* c, void* stream, double* mhz_out) {
+  if (!c || !mhz_out) return PBG_ERR_INVALID;
+  *mhz_out = 0.0;
+  Workspace& w = c->ws_bf16;
+  if (!w.sched) return fail(c, PBG_ERR_INVALID, "no bf16-mode pass has run on this ctx");
+  PBG_CUDA(c, cudaSetDevice(c->dims.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  PassSched h;
+  PBG_CUDA(c, cudaMemcpyAsync(&h, w.sched, sizeof h, cudaMemcpyDeviceToHost, s));
+  PBG_CUDA(c, cudaStreamSynchronize(s));
+  if (h.clk_ns > 0) *mhz_out = static_cast<double>(h.clk_ticks) / static_cast<double>(h.clk_ns) * 1e3;
   return PBG_OK;
 }
 

@@ -38,25 +38,42 @@ constexpr int kTkMaxK = 16;           // largest k of the filter path; above it 
 constexpr int kTkSampleStride = 8;    // every 8th 256-entity tile is sampled for the cut-off
 constexpr int kTkKeys = 16;           // best group keys a thread keeps per sample list (>= kTkMaxK)
 constexpr int kTkRescoreMax = 512;    // candidates per row the rescoring kernel takes; more: exact scan
-constexpr float kTkErrBound = 0.009f; // |bf16 score - exact score| <= 2^-8 (unit vectors, 8-bit mantissas) + key truncation + slack
+// |bf16 score - exact score| for unit vectors: both operands rounded to 8 significant bits (relative 2^-9 each) give
+// (2^-8 + 2^-18) * sum |q_i t_i| <= 0.003910 by Cauchy-Schwarz; + fp32 accumulation of 128 exact products (<= 1.5e-5)
+// + the sample keys' 5 truncated mantissa bits (<= 4e-6) = 0.00393; the rest is slack
+constexpr float kTkErrBound = 0.0045f;
 enum : int { TK_SAMPLE = 0, TK_SCAN = 1 };
 
 struct alignas(64) TopkParams {
   CUtensorMap tm_q;      // normalised queries bf16 [Bpad, 128]: box 64 x 128 rows
   CUtensorMap tm_t;      // normalised table   bf16 [Npad, 128]: box 64 x 128 rows (one CTA's half of a 256-entity tile)
   int n_rb;              // 256-row query blocks
-  int n_ranges;          // tile ranges (work item = query block x range)
-  int tiles_per_range;   // visited tiles per range
-  int n_tiles;           // visited tiles: every tile (scan) or every kTkSampleStride-th (sample)
+  int n_tiles;           // visited tiles per query block: every tile (scan) or every kTkSampleStride-th (sample)
   int tile_stride;       // table tile = visited tile * tile_stride
-  int n_items;           // n_rb * n_ranges
+  int total;             // work units = n_rb * n_tiles (one unit = one query block x one visited tile), query-block major
+  int span;              // units per CTA pair: pair p takes units [p * span, (p + 1) * span) -- whole device, equal shares
+  int n_ranges;          // list slots per (row, column half): the most pairs whose spans meet one query block
   long long N;           // valid entities
-  int* samp_keys;        // sample: [Bpad][n_ranges * 2][kTkKeys] best group keys, descending
+  int* samp_keys;        // sample: [Bpad][n_ranges * 2][kTkKeys] best group keys, descending (unused slots: zero)
   const float* tau;      // scan:   [Bpad] cut-off per query row
   unsigned* cand_grp;    // scan:   [Bpad][n_ranges * 2][kTkCand] 32-entity group numbers ...
   unsigned* cand_mask;   //         ... and which of the group's entities scored above tau
-  int* cand_cnt;         // scan:   [Bpad][n_ranges * 2] groups found (more than kTkCand: the list overflowed)
+  int* cand_cnt;         // scan:   [Bpad][n_ranges * 2] groups found (more than kTkCand: the list overflowed; unused slots: 0)
 };
+
+// A pair's span of work units, cut at query-block boundaries: segment = (query block, visited tiles [t0, t1), list slot).
+// The slot numbers the pairs that meet a query block in order, so every (row, slot) list has exactly one writer.
+struct TkSeg { int rb, t0, t1, slot; };
+__device__ __forceinline__ bool tk_next_seg(const TopkParams& p, int pair, int& u, TkSeg& s) {
+  const int end = min((pair + 1) * p.span, p.total);
+  if (u >= end) return false;
+  s.rb = u / p.n_tiles;
+  s.t0 = u - s.rb * p.n_tiles;
+  s.t1 = min(p.n_tiles, s.t0 + (end - u));
+  s.slot = pair - (s.rb * p.n_tiles) / p.span;
+  u += s.t1 - s.t0;
+  return true;
+}
 
 struct TkSmem {
   static constexpr int kQ = 2 * 128 * kBlockK * 2;        // this CTA's 128 query rows, 2 k-blocks
@@ -166,7 +183,6 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = static_cast<int>(blockIdx.x) >> 1;
-  const int npairs = static_cast<int>(gridDim.x) >> 1;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&p.tm_q);
@@ -191,16 +207,17 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
       const uint32_t lead_q_full = mapa_u32(smem_u32(q_full), 0);
       uint32_t stage = 0, phase = 0, qphase = 0;
-      for (int item = pair; item < p.n_items; item += npairs) {
-        const int rb = item / p.n_ranges, rg = item % p.n_ranges;
-        // the query tile of this item (the previous item's MMAs have finished with the buffer)
+      int u = pair * p.span;
+      TkSeg sg;
+      while (tk_next_seg(p, pair, u, sg)) {
+        const int rb = sg.rb;
+        // the query tile of this segment (the previous segment's MMAs have finished with the buffer)
         mbar_wait(q_empty, qphase ^ 1);
         if (leader) mbar_arrive_expect_tx(q_full, 2u * L::kQ);
         for (int kb = 0; kb < 2; ++kb)
           tma_load_2d_pair(smem + kb * (L::kQ / 2), &p.tm_q, lead_q_full, kb * kBlockK, rb * 256 + static_cast<int>(rank) * 128);
         qphase ^= 1;
-        const int t0 = rg * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
-        for (int t = t0; t < t1; ++t) {
+        for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * L::kT);
           uint8_t* st = smem + L::kStageOff + stage * L::kT;
@@ -217,13 +234,13 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, 256);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, qphase = 0;
-      for (int item = pair; item < p.n_items; item += npairs) {
-        const int rg = item % p.n_ranges;
+      int u = pair * p.span;
+      TkSeg sg;
+      while (tk_next_seg(p, pair, u, sg)) {
         mbar_wait(q_full, qphase);
         qphase ^= 1;
         tc_fence_after();
-        const int t0 = rg * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
-        for (int t = t0; t < t1; ++t) {
+        for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -249,10 +266,12 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
     // ------------------------------------------------------------ filter warps (both CTAs): one query row per thread
     const int wep = warp - 2, q = warp & 3, half = wep >> 2;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = pair; item < p.n_items; item += npairs) {
-      const int rb = item / p.n_ranges, rg = item % p.n_ranges;
+    int u = pair * p.span;
+    TkSeg sg;
+    while (tk_next_seg(p, pair, u, sg)) {
+      const int rb = sg.rb, rg = sg.slot;
       const long long row = static_cast<long long>(rb) * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
-      const int t0 = rg * p.tiles_per_range, t1 = min(p.n_tiles, t0 + p.tiles_per_range);
+      const int t0 = sg.t0, t1 = sg.t1;
       int m[kTkKeys];                       // sample: the best group keys so far, descending
 #pragma unroll
       for (int i = 0; i < kTkKeys; ++i) m[i] = 0;
@@ -321,6 +340,18 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
         for (int i = 0; i < kTkKeys; ++i) p.samp_keys[lbase * kTkKeys + i] = m[i];
       } else {
         p.cand_cnt[lbase] = cnt;
+      }
+      // the pair that finishes a query block empties the block's list slots that no pair wrote
+      if (t1 == p.n_tiles) {
+        for (int sl = rg + 1; sl < p.n_ranges; ++sl) {
+          const long long lb = row * (p.n_ranges * 2) + sl * 2 + half;
+          if (MODE == TK_SAMPLE) {
+#pragma unroll
+            for (int i = 0; i < kTkKeys; ++i) p.samp_keys[lb * kTkKeys + i] = 0;
+          } else {
+            p.cand_cnt[lb] = 0;
+          }
+        }
       }
     }
   }

@@ -23,7 +23,7 @@ SYMBOLS = (
     "pbg_discriminator_forward", "pbg_discriminator_score_triplets", "pbg_score_triplets",
     "pbg_score_triplets_host", "pbg_linear_bf16", "pbg_profile_enable", "pbg_profile_read", "pbg_debug_trace", "pbg_check_indices", "pbg_launch_count",
     "pbg_set_launch_width", "pbg_set_result_mirrors", "pbg_topk_prepare", "pbg_topk", "pbg_parse_index_rows", "pbg_format_f32_json", "pbg_format_i64_json",
-    "pbg_reserve", "pbg_stage_triplets", "pbg_score_staged", "pbg_set_result_multicast", "pbg_topk_last_flagged", "pbg_score_triplets_host_packed", "pbg_score_staged_stage_next", "pbg_set_workspace_discard",
+    "pbg_reserve", "pbg_stage_triplets", "pbg_score_staged", "pbg_set_result_multicast", "pbg_topk_last_flagged", "pbg_score_triplets_host_packed", "pbg_score_staged_stage_next", "pbg_set_workspace_discard", "pbg_last_pass_sm_clock",
 )
 
 
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
         "pbg_launch_count": (i64, [vp]),
         "pbg_set_launch_width": (C.c_int, [vp, i32]),
         "pbg_set_workspace_discard": (C.c_int, [vp, i32]),
+        "pbg_last_pass_sm_clock": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
         "pbg_set_result_mirrors": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "pbg_topk_prepare": (C.c_int, [vp, vp, i64, vp]),
         "pbg_topk": (C.c_int, [vp, vp, i64, i32, vp, vp, vp]),

@@ -21,6 +21,7 @@ class ClockSampler:
     def __init__(self, device_index: int = 0, period_s: float = 0.002):
         self.idx, self.period = device_index, period_s
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.power_w, self.power_limit_w, self.power_kind = [], None, "1 s average"
         self._stop = threading.Event()
         self._thread = None
         self._nvml = None
@@ -30,6 +31,10 @@ class ClockSampler:
             self._nvml = pynvml
             self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit_w = pynvml.nvmlDeviceGetEnforcedPowerLimit(self._h) / 1000.0
+            except Exception:
+                self.power_limit_w = None
         except Exception:
             self._nvml = None
 
@@ -37,6 +42,17 @@ class ClockSampler:
         n = self._nvml
         try:
             self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+            try:   # board power: the instantaneous field where the driver has it (nvmlDeviceGetPowerUsage is a 1 s average)
+                fv = n.nvmlDeviceGetFieldValues(self._h, [n.NVML_FI_DEV_POWER_INSTANT])[0]
+                if fv.nvmlReturn != 0:
+                    raise RuntimeError
+                self.power_w.append(fv.value.uiVal / 1000.0)
+                self.power_kind = "instant"
+            except Exception:
+                try:
+                    self.power_w.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                except Exception:
+                    pass
             mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(
                 n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
             for bit, name in _REASONS.items():
@@ -79,4 +95,8 @@ class ClockSampler:
             "sm_max_mhz": self.sm_max,
             "reasons": sorted(self.reasons),
             "samples": len(self.sm),
+            "power_w": round(statistics.median(self.power_w), 1) if self.power_w else None,
+            "power_w_max": round(max(self.power_w), 1) if self.power_w else None,
+            "power_limit_w": self.power_limit_w,
+            "power_kind": self.power_kind if self.power_w else None,
         }

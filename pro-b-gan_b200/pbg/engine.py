@@ -75,6 +75,14 @@ class Engine:
         """CTAs (SMs) one fused pass occupies; 0 = the whole device.  See include/pbg.h."""
         cabi.check(self._lib.pbg_set_launch_width(self._h, int(ctas)), self._h)
 
+    def last_pass_sm_clock(self) -> float:
+        """SM clock (MHz) during this ctx's last bf16-mode pass, measured in the kernel (include/pbg.h); synchronises."""
+        import ctypes
+        mhz = ctypes.c_double(0.0)
+        with torch.cuda.device(self.device):
+            cabi.check(self._lib.pbg_last_pass_sm_clock(self._h, self._stream(), ctypes.byref(mhz)), self._h)
+        return float(mhz.value)
+
     def set_workspace_discard(self, on: bool) -> None:
         """Dead activation row blocks are dropped from L2 instead of being written back to HBM (default on).  See include/pbg.h."""
         cabi.check(self._lib.pbg_set_workspace_discard(self._h, int(bool(on))), self._h)

@@ -358,6 +358,17 @@ def test_workspace_discard_does_not_change_a_single_bit(cuda_models, dev_tables,
     off.check_indices(); on.check_indices()
 
 
+def test_in_kernel_sm_clock_reading(cuda_models, dev_tables, synth, dev):
+    """pbg_last_pass_sm_clock: clock64() ticks per globaltimer nanosecond over CTA 0's lifetime -- a plausible SM clock."""
+    import modular_prot_b_gan as m
+    eng = m.make_fused_engine(*cuda_models)
+    trip, z = synth.make_triplets(4096).to(dev), synth.make_latents(4096).to(dev)
+    for _ in range(3):
+        _pass(eng, dev_tables, trip, z)
+    mhz = eng.last_pass_sm_clock()
+    assert 300.0 < mhz < 2500.0, mhz
+
+
 def test_passes_on_concurrent_lanes_match_sequential(cuda_models, dev_tables, synth, dev):
     """Three ctxs on three streams, 48 SMs each, passes in flight together (bench.py's lanes)."""
     import modular_prot_b_gan as m
