@@ -243,6 +243,47 @@ def time_gpu_library(cfg: dict, batch: int, dev, node_emb, rel_w) -> dict:
                 e2 = torch.cuda.Event(); e2.record(s); main.wait_event(e2)
         multi(); torch.cuda.synchronize()
         res["cuda_graph_4_streams"] = timed(multi, per * 5 * 4)
+        # The five GEMMs of one pass ALONE (cuBLASLt bf16 on these very shapes: no gather, bias, activation, cosine, hand-off),
+        # 4 graphs on 4 streams, regions of >= 60 ms, first region dropped: the library's sustained rate for this pass's
+        # matmuls -- the shape-limited ceiling beside MEASURED_PEAKS.json's 8192^3 figure (tools/bench_gemm_shapes.py).
+        E_, Z_, H_, HD_ = cfg["E"], cfg["Z"], cfg["H"], cfg.get("HD", cfg["H"])
+        shapes = [(2 * E_ + Z_, H_), (3 * E_, HD_), (H_, H_), (HD_, HD_ // 2), (H_, E_)]
+        g2 = []
+        for s_ in streams:
+            xs = [torch.randn(batch, k, device=dev, dtype=torch.bfloat16) for k, _ in shapes]
+            ws = [torch.randn(n_, k, device=dev, dtype=torch.bfloat16) for k, n_ in shapes]
+            os_ = [torch.empty(batch, n_, device=dev, dtype=torch.bfloat16) for _, n_ in shapes]
+            gg = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s_):
+                for x, w, o in zip(xs, ws, os_):
+                    torch.matmul(x, w.T, out=o)
+                s_.synchronize()
+                with torch.cuda.graph(gg, stream=s_):
+                    for _ in range(per):
+                        for x, w, o in zip(xs, ws, os_):
+                            torch.matmul(x, w.T, out=o)
+            g2.append((gg, xs, ws, os_))
+        torch.cuda.synchronize()
+
+        def gemms(n_rep):
+            def run():
+                main = torch.cuda.current_stream(dev)
+                e = torch.cuda.Event(); e.record(main)
+                for s_, (gg, *_) in zip(streams, g2):
+                    s_.wait_event(e)
+                    with torch.cuda.stream(s_):
+                        for _ in range(n_rep):
+                            gg.replay()
+                    e2 = torch.cuda.Event(); e2.record(s_); main.wait_event(e2)
+            return run
+        probe = timed(gemms(2), per * 2 * 4)                                   # samples/s-equivalent
+        n_rep = max(2, int(0.060 * probe / (per * 4 * batch)) + 1)
+        regions = [timed(gemms(n_rep), per * n_rep * 4) for _ in range(4)]
+        flop_sample = sum(2.0 * k * n_ for k, n_ in shapes)
+        res["gemms_only_4_streams"] = statistics.median(regions[1:])
+        res["gemms_only_tflops"] = res["gemms_only_4_streams"] * flop_sample / 1e12
+        res["gemms_only_what"] = ("torch.matmul bf16 on the pass's five GEMM shapes alone (" + ", ".join(f"{batch}x{k}x{n_}" for k, n_ in shapes) +
+                                  "), no gather / bias / activation / cosine: samples/s-equivalent, sustained (median of 3 regions of >= 60 ms after the first)")
     res["value"] = max(res["eager"], res["cuda_graph"], res["cuda_graph_4_streams"])
     return res
 
@@ -661,6 +702,10 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     lib = None
     if rank == 0 and world == 1 and not args.no_library_baseline:
         lib = time_gpu_library(cfg, B, dev, node_emb, rel_w)
+        if lib.get("gemms_only_tflops"):
+            # cuBLASLt on this pass's own GEMM shapes, same box, same power state: the shape-limited library rate
+            roofline["library_gemms_only_tflops"] = lib["gemms_only_tflops"]
+            roofline["frac_of_library_gemms_only"] = step_tflops / lib["gemms_only_tflops"]
 
     if rank == 0:
         cpu = None

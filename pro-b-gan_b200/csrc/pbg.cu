@@ -707,8 +707,17 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
   PBG_CUDA(c, cudaSetDevice(c->dims.device));
   cudaStream_t s = (cudaStream_t)stream;
   const int E = c->dims.embed_dim;
-  const long long kChunk = 16384;
-  const bool filter = E == 128 && k <= kTkMaxK && t.N >= 16 * 256;   // small tables / other shapes: the general path
+  // rows per round of launches.  A row's cut-off is the k-th best of its sampled group keys, 16 kept per (row, pair, column
+  // half) list: at 4096 rows a block is met by 5-6 pairs in the sample launch (160+ keys), at 16384 rows by 2-3 -- enough
+  // for k <= 16 only
+  const long long kChunk = k > 16 ? 4096 : 16384;
+  // small tables / other shapes: the general path.  The sample launch sees N / (32 stride) groups of 32 entities per row
+  // and the cut-off needs k positive group maxima among them: at least 2 k groups
+  // The cut-off is the k-th best score of a 1-in-`stride` sample of the table tiles, so about stride * k entities (+ a dozen
+  // inside the error margin) pass it and are rescored: the stride shrinks as k grows (k = 64 at 1 in 8: one row in a
+  // hundred had more than the 1024 candidates the rescoring kernel takes and went to the 3 ms exact scan).
+  const int stride = tk_sample_stride(k);
+  const bool filter = E == 128 && k <= kTkMaxK && t.N >= std::max<long long>(16 * 256, 64ll * stride * k);
   for (long long off = 0; off < B; off += kChunk) {
     const long long rows = std::min(kChunk, B - off);
     const long long rows_pad = (rows + 255) / 256 * 256;
@@ -756,8 +765,8 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
     TopkParams ps, pm;
     memset(&ps, 0, sizeof ps); memset(&pm, 0, sizeof pm);
     ps.tm_q = pm.tm_q = t.tm_q; ps.tm_t = pm.tm_t = t.tm_t; ps.N = pm.N = t.N;
-    ps.tile_stride = kTkSampleStride; pm.tile_stride = 1;
-    split((n_tiles + kTkSampleStride - 1) / kTkSampleStride, ps);
+    ps.tile_stride = stride; pm.tile_stride = 1;
+    split((n_tiles + stride - 1) / stride, ps);
     split(n_tiles, pm);
     const int n_slists = ps.n_ranges * 2, n_lists = pm.n_ranges * 2;
     const size_t need = static_cast<size_t>(rows_pad) * n_lists * kTkCand;
@@ -792,7 +801,7 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
       pbg_topk_scan_kernel<TK_SCAN><<<std::min(grid, 2 * ((pm.total + pm.span - 1) / pm.span)), kPassThreads, TkSmem::kTotal, s>>>(pm); }
     PBG_CUDA(c, cudaGetLastError());
     { LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_rescore_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask,
+      topk_rescore_kernel<<<static_cast<unsigned>((rows + kTkRescoreWarps - 1) / kTkRescoreWarps), 32 * kTkRescoreWarps, 0, s>>>(q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask,
                                                                                 t.cand_cnt, t.tau, n_lists, rows, t.N, k, oi, os, t.flag); }
     PBG_CUDA(c, cudaGetLastError());
     { // rows the filter could not prove: exact scan, one CTA per row (rare)

@@ -7,7 +7,7 @@
 // The [B, N] similarity matrix (1 GiB at B = 4096, N = 65536) never exists.  Steps (E = 128, k <= 16):
 //   1. prepare : row norms; bf16 copies of the normalised table / queries, zero padded to 256 rows        (HBM-bound)
 //   2. sample  : bf16 tensor-core scores (CTA pairs, tcgen05.mma.cta_group::2, M = 256 queries x N = 256 entities per
-//                MMA group, K = E = 128; query tile stationary, entity tiles streamed by TMA) of every 8th entity
+//                MMA group, K = E = 128; query tile stationary, entity tiles streamed by TMA) of every 8th entity (k <= 16; every 4th / 2nd for k <= 32 / 64)
 //                tile.  Epilogue per query row (one thread each): the maximum of every 32 scores as a packed
 //                (score | position) integer key -- one LOP3 per score and a three-input max tree -- pushed through a
 //                16-deep sorted insert once per 32 scores.  A small kernel merges a row's lists: tau[row] = the k-th
@@ -21,7 +21,7 @@
 //                everything that was not a candidate has a bf16 score <= tau -- else the row is flagged and re-done
 //                by an exact scan of the table (rare).
 // so the returned indices are those of an exact fp32 evaluation, not of the bf16 scores.
-// Other shapes (k > 16, E != 128, small tables): exact fp32 scores of a chunk of rows by the SIMT GEMM of the parity
+// Other shapes (k > 64, E != 128, small tables): exact fp32 scores of a chunk of rows by the SIMT GEMM of the parity
 // mode, then one selection CTA per row (pbg.cu: topk_general).
 #pragma once
 #include <cuda.h>
@@ -34,10 +34,12 @@ namespace pbg {
 constexpr int kTkStages = 4;          // entity tiles in flight per CTA (32 KB each: 128 entities x 128 dims bf16)
 constexpr int kTkCand = 256;          // (group, mask) entries kept per (row, entity range, column half), in global memory
 constexpr int kTkMaxRanges = 16;
-constexpr int kTkMaxK = 16;           // largest k of the filter path; above it the general path runs
-constexpr int kTkSampleStride = 8;    // every 8th 256-entity tile is sampled for the cut-off
-constexpr int kTkKeys = 16;           // best group keys a thread keeps per sample list (>= kTkMaxK)
-constexpr int kTkRescoreMax = 512;    // candidates per row the rescoring kernel takes; more: exact scan
+constexpr int kTkMaxK = 64;           // largest k of the filter path; above it the general path runs
+// every stride-th 256-entity tile is sampled for the cut-off: 1 in 8 up to k = 16, 1 in 4 up to 32, 1 in 2 up to 64
+inline int tk_sample_stride(int k) { return k <= 16 ? 8 : (k <= 32 ? 4 : 2); }
+constexpr int kTkKeys = 16;           // best group keys a thread keeps per sample list; a row's lists together hold >= 2 k keys (pbg.cu: chunk size)
+constexpr int kTkRescoreMax = 1024;   // candidates per row the rescoring kernel takes (about 8 k + a dozen arrive); more: exact scan
+constexpr int kTkRescoreWarps = 4;    // rows per rescoring CTA (32 KB of candidate scores / indices in shared memory)
 // |bf16 score - exact score| for unit vectors: both operands rounded to 8 significant bits (relative 2^-9 each) give
 // (2^-8 + 2^-18) * sum |q_i t_i| <= 0.003910 by Cauchy-Schwarz; + fp32 accumulation of 128 exact products (<= 1.5e-5)
 // + the sample keys' 5 truncated mantissa bits (<= 4e-6) = 0.00393; the rest is slack
@@ -48,7 +50,7 @@ struct alignas(64) TopkParams {
   CUtensorMap tm_q;      // normalised queries bf16 [Bpad, 128]: box 64 x 128 rows
   CUtensorMap tm_t;      // normalised table   bf16 [Npad, 128]: box 64 x 128 rows (one CTA's half of a 256-entity tile)
   int n_rb;              // 256-row query blocks
-  int n_tiles;           // visited tiles per query block: every tile (scan) or every kTkSampleStride-th (sample)
+  int n_tiles;           // visited tiles per query block: every tile (scan) or every tile_stride-th (sample)
   int tile_stride;       // table tile = visited tile * tile_stride
   int total;             // work units = n_rb * n_tiles (one unit = one query block x one visited tile), query-block major
   int span;              // units per CTA pair: pair p takes units [p * span, (p + 1) * span) -- whole device, equal shares
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(256) topk_prepare_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ 2 / 3. sample, scan
-// MODE TK_SAMPLE: visited tiles are every kTkSampleStride-th tile; per (row, range, column half) the kTkKeys best group
+// MODE TK_SAMPLE: visited tiles are every tile_stride-th tile; per (row, range, column half) the kTkKeys best group
 //                 keys go to samp_keys.  MODE TK_SCAN: every tile; (group, mask) candidate lists.
 // (score bits with the low 5 bits replaced by the position) as ONE lop3: (a & b) | c
 __device__ __forceinline__ int tk_key(uint32_t bits, int j) {
@@ -405,18 +407,18 @@ __global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ s
 // not a candidate has a bf16 score <= tau.  flag[row] = 1 asks for the exact scan (list overflow, too many or too few
 // candidates, proof failed).  Each lane scores one candidate at a time (its whole 128-dim dot, the normalised query
 // broadcast from shared memory): 32 candidates and 32 independent row reads in flight per warp, no shuffles.
-__global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restrict__ q, const float* __restrict__ inv_q,
+__global__ void __launch_bounds__(32 * kTkRescoreWarps) topk_rescore_kernel(const float* __restrict__ q, const float* __restrict__ inv_q,
                                                            const float* __restrict__ table, const float* __restrict__ inv_t,
                                                            const unsigned* __restrict__ cand_grp, const unsigned* __restrict__ cand_mask,
                                                            const int* __restrict__ cand_cnt, const float* __restrict__ tau,
                                                            int n_lists, long long B, long long N, int k,
                                                            long long* __restrict__ out_idx, float* __restrict__ out_score,
                                                            int* __restrict__ flag) {
-  __shared__ float es_s[8][kTkRescoreMax];
-  __shared__ int ei_s[8][kTkRescoreMax];
+  __shared__ float es_s[kTkRescoreWarps][kTkRescoreMax];
+  __shared__ int ei_s[kTkRescoreWarps][kTkRescoreMax];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* es = es_s[w]; int* ei = ei_s[w];
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + w;
+  const long long row = static_cast<long long>(blockIdx.x) * kTkRescoreWarps + w;
   if (row >= B) return;
   // this lane's four dimensions of the normalised query stay in registers
   float4 qv = *reinterpret_cast<const float4*>(q + row * 128 + 4 * lane);

@@ -123,7 +123,7 @@ class Engine:
             raise RuntimeError(f"top_k must be positive, got {k}")
         if k > cls.MAX_TOP_K:
             raise NotImplementedError(f"top_k = {k}: the CUDA path selects at most {cls.MAX_TOP_K} per row "
-                                      "(k <= 16 on the tensor-core filter, above that exact fp32 scores + selection)")
+                                      "(k <= 64 on the tensor-core filter, above that exact fp32 scores + selection)")
 
     def set_result_mirrors(self, gen_out=(), gen_scores=(), logits=(), probs=()) -> None:
         """Device addresses (ints) of up to 7 mirror buffers per result, e.g. peer GPUs' windows: every bf16-mode

@@ -57,6 +57,20 @@ def test_topk_large_k_and_other_width_take_the_general_path(dev):
         m.cosine_topk(torch.randn(4, 128).to(dev), torch.randn(2000, 128).to(dev), 513)
 
 
+def test_topk_k17_to_64_on_the_filter_path(dev):
+    """k = 17 .. 64 stays on the tensor-core filter when the table is large enough (N >= 512 k): cut-off from the
+    sampled group keys (16 kept per list, 4096-row chunks so that a row has >= 10 lists), up to 1024 rescored candidates."""
+    import modular_prot_b_gan as m
+    g = torch.Generator().manual_seed(77)
+    q, t = torch.randn(4100, 128, generator=g), torch.randn(65536, 128, generator=g)   # two chunks, the second ragged
+    check(q, t, 40, dev, min_exact=0.5)
+    eng = [e for (_, width), e in m._TOPK_ENGINES.items() if width == 128][0]
+    n_flagged = eng.topk_last_flagged()
+    assert n_flagged == 0, eng.topk_flag_report     # the filter proved every row of the last chunk
+    check(torch.randn(300, 128, generator=g), torch.randn(40000, 128, generator=g), 64, dev, min_exact=0.3)
+    check(torch.randn(64, 128, generator=g), torch.randn(9000, 128, generator=g), 17, dev, min_exact=0.6)
+
+
 def test_topk_k16_on_the_filter_path_and_ragged_sizes(dev):
     g = torch.Generator().manual_seed(21)
     check(torch.randn(1000, 128, generator=g), torch.randn(65536, 128, generator=g), 16, dev)
