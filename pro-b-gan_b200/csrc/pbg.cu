@@ -127,6 +127,8 @@ struct pbg_ctx {
   long long launches = 0;
   int launch_ctas = 0;  // pbg_set_launch_width; 0 = all SMs
   int discard = 1;      // pbg_set_workspace_discard (PBG_DISCARD sets the initial value)
+  bool host_block = false;          // PBG_HOST_SYNC=block: the *_host entry points sleep on an event instead of spinning
+  cudaEvent_t host_evt = nullptr;   // cudaEventBlockingSync
   int n_mirror = 0;     // pbg_set_result_mirrors
   void* mir_gen[kMaxMirrors] = {}; float* mir_cos[kMaxMirrors] = {}; float* mir_logits[kMaxMirrors] = {}; float* mir_probs[kMaxMirrors] = {};
   void* mc_gen = nullptr; float *mc_cos = nullptr, *mc_logits = nullptr, *mc_probs = nullptr;   // pbg_set_result_multicast
@@ -753,11 +755,16 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
     // work units = query block x visited tile, query-block major; every pair takes an equal, contiguous span of them
     // (cut at query-block boundaries inside the kernel), so all SMs scan the same number of tiles whatever B is.  A
     // query block met by s pairs needs s list slots per row: the span is at least tiles / (kTkMaxRanges - 1).
-    auto split = [&](int tiles, TopkParams& p) {
+    auto split = [&](int tiles, TopkParams& p, bool align) {
       p.n_rb = n_rb;
       p.n_tiles = tiles;
       p.total = n_rb * tiles;
       p.span = std::max({1, (p.total + npairs - 1) / npairs, (tiles + kTkMaxRanges - 2) / (kTkMaxRanges - 1)});
+      // A span that crosses a query-block boundary costs its pair a second segment (new query tile, lists closed and
+      // reopened: ~5 us).  The scan launch (56 tiles per pair at B = 4096) gains more from all 74 pairs being busy than
+      // it loses (61 against 66 us); the sample launch (7 tiles per pair) does not (24 against 17 us), so its span is
+      // rounded up to divide a query block's tiles: one segment per pair, fewer pairs.
+      if (align && p.span < tiles) { const int pieces = std::max(1, tiles / p.span); p.span = (tiles + pieces - 1) / pieces; }
       p.n_ranges = 1;
       for (int rb = 0; rb < n_rb; ++rb)
         p.n_ranges = std::max(p.n_ranges, ((rb + 1) * tiles - 1) / p.span - (rb * tiles) / p.span + 1);
@@ -766,8 +773,8 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
     memset(&ps, 0, sizeof ps); memset(&pm, 0, sizeof pm);
     ps.tm_q = pm.tm_q = t.tm_q; ps.tm_t = pm.tm_t = t.tm_t; ps.N = pm.N = t.N;
     ps.tile_stride = stride; pm.tile_stride = 1;
-    split((n_tiles + stride - 1) / stride, ps);
-    split(n_tiles, pm);
+    split((n_tiles + stride - 1) / stride, ps, true);
+    split(n_tiles, pm, false);
     const int n_slists = ps.n_ranges * 2, n_lists = pm.n_ranges * 2;
     const size_t need = static_cast<size_t>(rows_pad) * n_lists * kTkCand;
     const size_t sneed = static_cast<size_t>(rows_pad) * n_slists * kTkKeys;
@@ -903,6 +910,7 @@ int pbg_create(pbg_ctx** out, const pbg_dims* dims) {
   c->dims = *dims;
   c->num_sms = prop.multiProcessorCount;
   if (const char* e = getenv("PBG_DISCARD")) c->discard = atoi(e) != 0;
+  if (const char* e = getenv("PBG_HOST_SYNC")) c->host_block = strcmp(e, "block") == 0;
   c->kg0 = 2 * E + Z; c->kg0p = round_up(c->kg0, kBlockK);
   c->kd0 = 3 * E;     c->kd0p = round_up(c->kd0, kBlockK);
   c->hgp = round_up(HG, 128); c->hdp = round_up(HD, 128);
@@ -945,6 +953,7 @@ void pbg_destroy(pbg_ctx* c) {
   cudaFree(c->tk.samp_keys); cudaFree(c->tk.tau); cudaFree(c->tk.score_buf);
 
   if (c->err_flag_host) cudaFreeHost(c->err_flag_host);
+  if (c->host_evt) cudaEventDestroy(c->host_evt);
   cudaFree(c->st_block);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -1243,7 +1252,15 @@ int pbg_check_indices(pbg_ctx* c, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   PBG_CUDA(c, cudaSetDevice(c->dims.device));
   PBG_CUDA(c, cudaMemcpyAsync(c->err_flag_host, c->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PBG_CUDA(c, cudaStreamSynchronize(s));
+  if (c->host_block) {
+    // PBG_HOST_SYNC=block: the calling thread sleeps until the stream has drained instead of spinning on it -- for hosts
+    // with fewer cores than synchronous callers (8 ranks x 6 threads on 32 cores); costs a wake-up latency per call
+    if (!c->host_evt) PBG_CUDA(c, cudaEventCreateWithFlags(&c->host_evt, cudaEventBlockingSync | cudaEventDisableTiming));
+    PBG_CUDA(c, cudaEventRecord(c->host_evt, s));
+    PBG_CUDA(c, cudaEventSynchronize(c->host_evt));
+  } else {
+    PBG_CUDA(c, cudaStreamSynchronize(s));
+  }
   if (*c->err_flag_host != 0) {
     PBG_CUDA(c, cudaMemsetAsync(c->err_flag, 0, sizeof(int), s));
     PBG_CUDA(c, cudaStreamSynchronize(s));

@@ -78,9 +78,10 @@ __device__ __forceinline__ bool tk_next_seg(const TopkParams& p, int pair, int& 
 }
 
 struct TkSmem {
-  static constexpr int kQ = 2 * 128 * kBlockK * 2;        // this CTA's 128 query rows, 2 k-blocks
+  static constexpr int kQ = 2 * 128 * kBlockK * 2;        // this CTA's 128 query rows, 2 k-blocks; TWO such buffers: the next
+                                                          // segment's query tile lands while this segment's tiles stream
   static constexpr int kT = 2 * 128 * kBlockK * 2;        // this CTA's 128 entities of a tile, 2 k-blocks
-  static constexpr int kStageOff = kQ;
+  static constexpr int kStageOff = 2 * kQ;
   static constexpr int kBarOff = kStageOff + kTkStages * kT;
   static constexpr int kTotal = kBarOff + 256 + 1024;
 };
@@ -176,9 +177,9 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
   uint64_t* empty_bar = full_bar + kTkStages;
   uint64_t* tmem_full = empty_bar + kTkStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* q_full = tmem_empty + 2;
-  uint64_t* q_empty = q_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
+  uint64_t* q_full = tmem_empty + 2;     // [2]
+  uint64_t* q_empty = q_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -191,8 +192,7 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
     prefetch_tmap(&p.tm_t);
     for (int s = 0; s < kTkStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 2 * kEpiWarps); }
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
@@ -208,17 +208,19 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
     if (lane == 0) {
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
       const uint32_t lead_q_full = mapa_u32(smem_u32(q_full), 0);
-      uint32_t stage = 0, phase = 0, qphase = 0;
+      uint32_t stage = 0, phase = 0, nseg = 0;
       int u = pair * p.span;
       TkSeg sg;
       while (tk_next_seg(p, pair, u, sg)) {
         const int rb = sg.rb;
-        // the query tile of this segment (the previous segment's MMAs have finished with the buffer)
-        mbar_wait(q_empty, qphase ^ 1);
-        if (leader) mbar_arrive_expect_tx(q_full, 2u * L::kQ);
+        // the query tile of this segment into buffer nseg & 1 (free once the MMAs of segment nseg - 2 are done: this
+        // thread runs a ring ahead of the MMAs, so the tile is in flight while the previous segment still computes)
+        const uint32_t qb = nseg & 1, qphase = (nseg >> 1) & 1;
+        mbar_wait(&q_empty[qb], qphase ^ 1);
+        if (leader) mbar_arrive_expect_tx(&q_full[qb], 2u * L::kQ);
         for (int kb = 0; kb < 2; ++kb)
-          tma_load_2d_pair(smem + kb * (L::kQ / 2), &p.tm_q, lead_q_full, kb * kBlockK, rb * 256 + static_cast<int>(rank) * 128);
-        qphase ^= 1;
+          tma_load_2d_pair(smem + qb * L::kQ + kb * (L::kQ / 2), &p.tm_q, lead_q_full + qb * 8, kb * kBlockK, rb * 256 + static_cast<int>(rank) * 128);
+        ++nseg;
         for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * L::kT);
@@ -235,19 +237,20 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
     // ------------------------------------------------------------ MMA issuer (leader)
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(256, 256);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, qphase = 0;
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, nseg = 0;
       int u = pair * p.span;
       TkSeg sg;
       while (tk_next_seg(p, pair, u, sg)) {
-        mbar_wait(q_full, qphase);
-        qphase ^= 1;
+        const uint32_t qb = nseg & 1;
+        mbar_wait(&q_full[qb], (nseg >> 1) & 1);
+        ++nseg;
         tc_fence_after();
         for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * 256;
-          const uint32_t sq = smem_u32(smem), stt = smem_u32(smem + L::kStageOff + stage * L::kT);
+          const uint32_t sq = smem_u32(smem + qb * L::kQ), stt = smem_u32(smem + L::kStageOff + stage * L::kT);
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
             const uint64_t da = make_kmajor_sw128_desc(sq + kb * (L::kQ / 2));
@@ -260,7 +263,7 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
           if (++stage == kTkStages) { stage = 0; phase ^= 1; }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit_pair(q_empty, 3);   // the query tile may be overwritten once these MMAs are done
+        umma_commit_pair(&q_empty[qb], 3);   // this query buffer may be overwritten once these MMAs are done
       }
     }
     __syncwarp();
