@@ -601,7 +601,10 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
         hp.append(blk)
     # a synchronous call spends most of its life in PCIe copies and the completion wake-up, so the server model is
     # more calls in flight than passes fit on the device: T host threads (default one per lane; --e2e-threads), one ctx each
-    T = args.e2e_threads if args.e2e_threads > 0 else S
+    # (a synchronous call spins in cudaStreamSynchronize: every caller wants a core of its own -- with 8 ranks on one box the
+    # default is what the host's cores allow; PBG_HOST_SYNC=block sleeps instead and measured 79-118 M against 149 M at N = 1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    T = args.e2e_threads if args.e2e_threads > 0 else max(2, min(S, cores // max(world, 1)))
     for e in engines:
         e.set_result_mirrors()   # host results need no re-assembly: every rank's caller receives its own shard
         e.set_result_multicast()
@@ -639,7 +642,7 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
            "h2d_bytes_per_step": B * (3 * 8 + Z * 4) * world, "d2h_bytes_per_step": B * 3 * 4 * world,
            "steps": Ke, "seconds": e2e_s,
            "api": f"pbg_score_triplets_host_packed (C ABI, pinned host blocks [triplets | z] in and [scores | logits | probs] out: one copy per direction, one sync per call), "
-                  f"{T} host thread(s), one ctx each; wall clock over {Ke} calls (>= --steps, long enough for "
+                  f"{T} host thread(s) per rank ({cores} host cores, {world} rank(s)), one ctx each; wall clock over {Ke} calls (>= --steps, long enough for "
                   f"{args.e2e_min_s} s)"}
 
     # ---- roofline of the dominant kernel: per-kernel CUDA events on its launch stream, the same lanes in flight
