@@ -28,6 +28,9 @@
 // producers never wait between an item's loads: every stage is refilled with W and A the moment it frees.
 // The gather of every row is "phase 0" of the epilogue warps.
 //
+// A workspace row block that its consumer layer has finished with is dropped from L2 (discard.global.L2) by the epilogue
+// warps that can prove it dead from the dependency counters, so dead activations are never written back to HBM (p2_discard).
+//
 // Epilogues: bias + LeakyReLU -> bf16 -> swizzled staging (double-buffered per warp) -> TMA store; the final
 // discriminator dot and the cosine against the tail embedding are written as per-64-column partials that the last
 // warp to arrive for the 256-row block sums in a fixed order (bit-identical for any batch size / interleaving).
