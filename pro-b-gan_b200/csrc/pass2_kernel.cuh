@@ -484,7 +484,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         // the previous item's LAST stage has freed, and its proxy fence then waits for its own bulk loads in flight:
         // 3-4 thousand clocks of tensor-pipe idle per tile boundary, tools/ubench_pipe.cu vs the r1f trace.)
         if ((it.x & 0xff) != IT_END) p2_poll_dep(p, p.layer[it.x & 0xff].dep_kind, static_cast<int>(it.y));
-        mbar_wait(&sched_empty[slot], sphase ^ 1);
+        mbar_wait_role(&sched_empty[slot], sphase ^ 1);
         ring[slot] = it;
         mbar_arrive(&sched_full[slot]);
         mbar_arrive_cluster(lead_sched_full + slot * 8);  // release at cluster scope: the slot is visible to the remote loads
@@ -500,7 +500,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       long long w_dep = 0, w_empty = 0, n_items = 0;
       const uint32_t lead_full = mapa_u32(smem_u32(full_bar), 0);
       for (;;) {
-        mbar_wait(&sched_full[slot], sphase);
+        mbar_wait_role(&sched_full[slot], sphase);
         const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
         mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
@@ -517,8 +517,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         const int a_row = rb * kP2Rows + static_cast<int>(rank) * 128;
         const int w_row = n_blk * ly.block_n + static_cast<int>(rank) * w_rows;
         for (int kb = 0; kb < ly.num_kb; ++kb) {
-          if (tr) { const long long t = clock64(); mbar_wait(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
-          else mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (tr) { const long long t = clock64(); mbar_wait_role(&empty_bar[stage], phase ^ 1); w_empty += clock64() - t; }
+          else mbar_wait_role(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStage;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], bytes_pair);
           if (tr) t_issue[stage] = clock64();
@@ -537,8 +537,8 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0, lat_sum = 0, lat_n = 0, lat_max = 0;
       int n_it = 0;
       for (;;) {
-        if (tr) { const long long t = clock64(); mbar_wait(&sched_full[slot], sphase); w_item += clock64() - t; }
-        else mbar_wait(&sched_full[slot], sphase);
+        if (tr) { const long long t = clock64(); mbar_wait_role(&sched_full[slot], sphase); w_item += clock64() - t; }
+        else mbar_wait_role(&sched_full[slot], sphase);
         const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
         mbar_arrive_remote(sched_empty_addr + slot * 8 + ring_dep(it));
         if (++slot == kP2Ring) { slot = 0; sphase ^= 1; }
@@ -546,19 +546,19 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (kind == IT_END) break;
         const P2Layer& ly = p.layer[kind];
         const uint32_t idesc = make_idesc_bf16(kP2Rows, static_cast<uint32_t>(ly.block_n));
-        if (tr) { const long long t = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
-        else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (tr) { const long long t = clock64(); mbar_wait_role(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
+        else mbar_wait_role(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         if (tr && n_it < kTraceItems) tr[16 + 4 * n_it + 1] = clock64();   // this item's accumulator stage is free: MMA start
         ++n_it;
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = 0; kb < ly.num_kb; ++kb) {
           if (tr) {
-            const long long t = clock64(); mbar_wait(&full_bar[stage], phase); const long long t1 = clock64();
+            const long long t = clock64(); mbar_wait_role(&full_bar[stage], phase); const long long t1 = clock64();
             w_full += t1 - t; ++n_kb;
             const long long lat = t1 - t_issue[stage];
             if (t1 - t > 64) { lat_sum += lat; lat_n += 1; if (lat > lat_max) lat_max = lat; }  // only when the MMA really waited
-          } else mbar_wait(&full_bar[stage], phase);
+          } else mbar_wait_role(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStage);
           const uint64_t da = make_kmajor_sw128_desc(sa);

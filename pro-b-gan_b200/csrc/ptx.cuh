@@ -49,7 +49,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #define PBG_TRY_WAIT_HINT_NS 10000000
 #endif
 constexpr uint32_t kTryWaitHintNs = PBG_TRY_WAIT_HINT_NS;
-// hang guard: rounds of try_wait before a wait traps (a round may last up to the hint; several seconds in total)
+// hang guard: rounds of try_wait before a wait traps.  With nothing happening in the CTA a round lasts the whole hint
+// (4000 x 10 ms: a hung pass traps after 40 s), but a suspended try_wait also returns whenever another mbarrier of the
+// CTA completes a phase -- a wait that legitimately spans N k-blocks of the main loop sees about 2 N rounds (measured with
+// tools/ubench_pipe.cu: a 4096-k-block wait ran out of 4000 rounds).  The kernels' longest waits span one tile
+// (<= 64 k-blocks); tools that wait across a whole kernel build with a short hint (-DPBG_TRY_WAIT_HINT_NS=1000).
 constexpr uint32_t kGuardSpins = kTryWaitHintNs >= 1000000u ? 4000u : 4000000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -100,6 +104,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
+}
+
+// Blocking wait of a single-thread role that everything else waits for (TMA producer, MMA issuer, scheduler).
+// PBG_ROLE_WAIT_SHORT=1 (experiment) uses try_wait WITHOUT the suspend-time hint for them: the isolated main loop
+// (tools/ubench_pipe.cu) runs 546 clk per k-block with the hint and 513 without (floor 512) -- a parked thread takes tens of
+// clocks longer to resume -- but in the pass kernel the spinning threads cost more than they return: 173.3 M samples/s
+// against 177.0 M with the hint (same box, alternating runs), a staged lone pass 61.8 against 58.8 us.  Off.
+#ifndef PBG_ROLE_WAIT_SHORT
+#define PBG_ROLE_WAIT_SHORT 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity) {
+#if PBG_ROLE_WAIT_SHORT
+#if PBG_HANG_GUARD
+  uint32_t spins = 0;
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if (++spins > 40000000u) pbg_wait_timed_out("role mbarrier (parity, offset)", parity, smem_u32(bar) & 0x3ffu);
+  }
+#else
+  while (!mbar_try_wait_nohint(bar, parity)) {
+  }
+#endif
+#else
+  mbar_wait(bar, parity);
 #endif
 }
 

@@ -3,7 +3,8 @@
 // through an S-stage ring, no epilogue.  Answers: what does this loop sustain per K-block (MMA floor: 512 clk) as a
 // function of ring depth and of how many SMs pull from L2 at once?  Optional extra shared-memory traffic per K-block
 // (generic stores by 8 idle warps) imitates the epilogues' staging writes.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o tools/ubench_pipe tools/ubench_pipe.cu -lcuda
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -DPBG_TRY_WAIT_HINT_NS=1000 -o tools/ubench_pipe tools/ubench_pipe.cu -lcuda
+//        (the short wait hint keeps the hang guard at 4 M rounds: the peer CTA waits on one barrier across the whole kernel)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -139,7 +140,22 @@ void run(const CUtensorMap& ta, const CUtensorMap& tw, int grid, int n_kb, int a
          STAGES, EXTRA, grid, best, flop / best * 1e-9, mean / n_kb, mx / n_kb, wt / n_kb, 2.0 * kBox * n_kb / mean);
 }
 
-int main() {
+// random bf16 values in (-1, 1) with full-entropy mantissas (a hash of the element index), two per 32-bit word
+__global__ void fill_random_bf16(uint32_t* p, size_t n_words, uint32_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = static_cast<uint32_t>(i) * 2654435761u + seed;
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    // per half: sign from the hash, exponent 0x7c..0x7e (|v| in [0.125, 1)), 7 random mantissa bits
+    const uint32_t lo = (x & 0x8000u) | ((0x7cu + ((x >> 7) % 3u)) << 7) | (x & 0x7fu);
+    const uint32_t hi = ((x >> 16) & 0x8000u) | ((0x7cu + ((x >> 23) % 3u)) << 7) | ((x >> 16) & 0x7fu);
+    p[i] = lo | (hi << 16);
+  }
+}
+
+int main(int argc, char** argv) {
+  // ./ubench_pipe [random]: constant operand values (0x1111 everywhere) or random bf16 -- the same addresses, bytes and
+  // instructions either way; what changes is how many bits toggle in the tensor pipe
+  const bool random_data = argc > 1 && argv[1][0] == 'r';
   CK(cudaSetDevice(0));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -151,6 +167,12 @@ int main() {
   void *abuf, *wbuf;
   CK(cudaMalloc(&abuf, (size_t)a_blocks * 256 * 2048)); CK(cudaMemset(abuf, 0x11, (size_t)a_blocks * 256 * 2048));
   CK(cudaMalloc(&wbuf, (size_t)1024 * 2048)); CK(cudaMemset(wbuf, 0x11, (size_t)1024 * 2048));
+  if (random_data) {
+    fill_random_bf16<<<1184, 256>>>(static_cast<uint32_t*>(abuf), (size_t)a_blocks * 256 * 2048 / 4, 1u);
+    fill_random_bf16<<<1184, 256>>>(static_cast<uint32_t*>(wbuf), (size_t)1024 * 2048 / 4, 2u);
+    CK(cudaDeviceSynchronize());
+  }
+  printf("operand values: %s\n", random_data ? "random bf16 in (-1, 1)" : "constant (0x1111)");
   long long* d_cyc; CK(cudaMalloc(&d_cyc, sizeof(long long) * 1024));
   const CUtensorMap ta = make_map(enc, abuf, (uint64_t)a_blocks * 256, 1024), tw = make_map(enc, wbuf, 1024, 1024);
   const int n_kb = 4096;
