@@ -74,6 +74,15 @@ constexpr int kP2GatherPerBlock = 4;                // gather items per block: 6
 constexpr int kP2WarpsPerPair = 2 * kP2Epi;
 constexpr int kMaxMirrors = 7;                      // peers of an 8-GPU box
 
+// -DPBG_KB_PROBE=1 (diagnostics build, tools only): the MMA issuer of every leader CTA times its k-block loops per layer
+// with two clock reads per TILE -- the production instance otherwise unchanged -- and launch 30 of a process prints them.
+#ifndef PBG_KB_PROBE
+#define PBG_KB_PROBE 0
+#endif
+#if PBG_KB_PROBE
+__device__ int g_probe_n;
+#endif
+
 struct P2Layer {
   int num_kb;        // K / 64
   int block_n;       // UMMA N of this layer's pair tiles (128 / 256)
@@ -536,7 +545,15 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, slot = 0, sphase = 0;
       long long w_full = 0, w_tmem = 0, w_item = 0, n_kb = 0, lat_sum = 0, lat_n = 0, lat_max = 0;
       int n_it = 0;
+#if PBG_KB_PROBE
+      long long pr_clk[5] = {0, 0, 0, 0, 0}, pr_item = 0, pr_tmem = 0;
+      int pr_tiles[5] = {0, 0, 0, 0, 0};
+      const long long pr_begin = clock64();
+#endif
       for (;;) {
+#if PBG_KB_PROBE
+        const long long pr_t0 = clock64();
+#endif
         if (tr) { const long long t = clock64(); mbar_wait_role(&sched_full[slot], sphase); w_item += clock64() - t; }
         else mbar_wait_role(&sched_full[slot], sphase);
         const uint2 it = ld_cluster_u32x2(ring_addr + slot * 8);
@@ -546,9 +563,16 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         if (kind == IT_END) break;
         const P2Layer& ly = p.layer[kind];
         const uint32_t idesc = make_idesc_bf16(kP2Rows, static_cast<uint32_t>(ly.block_n));
+#if PBG_KB_PROBE
+        const long long pr_t1 = clock64();
+#endif
         if (tr) { const long long t = clock64(); mbar_wait_role(&tmem_empty[acc], acc_phase ^ 1); w_tmem += clock64() - t; }
         else mbar_wait_role(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+#if PBG_KB_PROBE
+        const long long pr_t2 = clock64();
+        pr_item += pr_t1 - pr_t0; pr_tmem += pr_t2 - pr_t1;
+#endif
         if (tr && n_it < kTraceItems) tr[16 + 4 * n_it + 1] = clock64();   // this item's accumulator stage is free: MMA start
         ++n_it;
         const uint32_t d_tmem = tmem_base + acc * 256;
@@ -570,7 +594,22 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
         }
         umma_commit_pair(&tmem_full[acc], 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+#if PBG_KB_PROBE
+        pr_clk[kind] += clock64() - pr_t2; pr_tiles[kind] += 1;
+#endif
       }
+#if PBG_KB_PROBE
+      {
+        const int n = atomicAdd(&g_probe_n, 1), npairs = static_cast<int>(gridDim.x) / 2, pair = static_cast<int>(blockIdx.x) / 2;
+        if (n / npairs == 30 && (pair == 0 || pair == npairs / 2 || pair == npairs - 1))
+          printf("probe pair %d of %d (M=%d): MMA thread lifetime %lld clk; waiting for an item %lld, for a free accumulator %lld; "
+                 "k-block loops (tiles: clk per tile) G.L0 %d: %lld  D.L0 %d: %lld  G.L1 %d: %lld  D.L1 %d: %lld  G.L2 %d: %lld\n",
+                 pair, npairs, p.M, clock64() - pr_begin, pr_item, pr_tmem,
+                 pr_tiles[0], pr_tiles[0] ? pr_clk[0] / pr_tiles[0] : 0, pr_tiles[1], pr_tiles[1] ? pr_clk[1] / pr_tiles[1] : 0,
+                 pr_tiles[2], pr_tiles[2] ? pr_clk[2] / pr_tiles[2] : 0, pr_tiles[3], pr_tiles[3] ? pr_clk[3] / pr_tiles[3] : 0,
+                 pr_tiles[4], pr_tiles[4] ? pr_clk[4] / pr_tiles[4] : 0);
+      }
+#endif
       if (tr) { tr[3] = w_full; tr[4] = w_tmem; tr[6] = clock64(); tr[9] = n_kb; tr[15] = w_item; tr[237] = lat_sum; tr[238] = lat_n; tr[239] = lat_max; }
     }
     __syncwarp();
