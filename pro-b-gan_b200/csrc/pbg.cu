@@ -604,6 +604,26 @@ int run_pass(pbg_ctx* c, const Pass& a) {
 
 }  // namespace
 
+namespace {
+// launch with programmatic stream serialisation (pdl): the kernel may begin while its predecessor on the stream drains; it
+// orders itself behind the predecessor with griddepcontrol.wait (topk_kernel.cuh: pdl_wait).  Used for the kernels of
+// one CTA per SM (sample, scan: their prologue -- barriers, TMEM, descriptors -- overlaps the predecessor's tail) and for
+// the exact-scan launch.  NOT for the cut-off and rescoring kernels: their many small blocks, released early, pile onto
+// whichever SMs the cluster kernel before them left idle (20 of 148 behind the sample launch, 34 behind a 1024-row scan)
+// instead of spreading over the device -- measured per link at k = 64: cut-off +12 / +32 us at B = 1024 / 4096, rescore
+// +33 us at B = 1024; sample, scan, exact: -3 us each (B = 256, k = 10: 84.5 -> 76 us).
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+}  // namespace
+
 extern "C" {
 
 int pbg_abi_version(void) { return PBG_ABI_VERSION; }
@@ -689,7 +709,7 @@ int topk_general(pbg_ctx* c, TopkState& t, const float* q, long long rows, int k
     PBG_CUDA(c, cudaGetLastError());
     { LaunchScope ls(c, PBG_K_OTHER, s);
       topk_exact_kernel<<<static_cast<unsigned>(r), threads, smem, s>>>(q + off * E, t.inv_q + off, t.table, t.inv_t, t.N, E, k,
-                                                                        nullptr, 1, t.score_buf, oi + off * k, os + off * k); }
+                                                                        nullptr, 1, t.score_buf, oi + off * k, os + off * k, r); }
     PBG_CUDA(c, cudaGetLastError());
   }
   return PBG_OK;
@@ -799,23 +819,18 @@ int pbg_topk(pbg_ctx* c, const float* queries, int64_t B, int k, int64_t* out_id
       attr_dev = c->dims.device;
     }
     { LaunchScope ls(c, PBG_K_TOPK, s);
-      pbg_topk_scan_kernel<TK_SAMPLE><<<std::min(grid, 2 * ((ps.total + ps.span - 1) / ps.span)), kPassThreads, TkSmem::kTotal, s>>>(ps); }
-    PBG_CUDA(c, cudaGetLastError());
+      PBG_CUDA(c, launch_pdl(true, pbg_topk_scan_kernel<TK_SAMPLE>, std::min(grid, 2 * ((ps.total + ps.span - 1) / ps.span)), kPassThreads, TkSmem::kTotal, s, ps)); }
     { LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_tau_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(t.samp_keys, n_slists, rows, rows_pad, k, t.tau); }
-    PBG_CUDA(c, cudaGetLastError());
+      PBG_CUDA(c, launch_pdl(false, topk_tau_kernel, static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s, t.samp_keys, n_slists, rows, rows_pad, k, t.tau)); }
     { LaunchScope ls(c, PBG_K_TOPK, s);
-      pbg_topk_scan_kernel<TK_SCAN><<<std::min(grid, 2 * ((pm.total + pm.span - 1) / pm.span)), kPassThreads, TkSmem::kTotal, s>>>(pm); }
-    PBG_CUDA(c, cudaGetLastError());
+      PBG_CUDA(c, launch_pdl(true, pbg_topk_scan_kernel<TK_SCAN>, std::min(grid, 2 * ((pm.total + pm.span - 1) / pm.span)), kPassThreads, TkSmem::kTotal, s, pm)); }
     { LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_rescore_kernel<<<static_cast<unsigned>((rows + kTkRescoreWarps - 1) / kTkRescoreWarps), 32 * kTkRescoreWarps, 0, s>>>(q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask,
-                                                                                t.cand_cnt, t.tau, n_lists, rows, t.N, k, oi, os, t.flag); }
-    PBG_CUDA(c, cudaGetLastError());
+      PBG_CUDA(c, launch_pdl(false, topk_rescore_kernel, static_cast<unsigned>((rows + kTkRescoreWarps - 1) / kTkRescoreWarps), 32 * kTkRescoreWarps, 0, s,
+                             q, t.inv_q, t.table, t.inv_t, t.cand_grp, t.cand_mask, t.cand_cnt, t.tau, n_lists, rows, t.N, k, oi, os, t.flag)); }
     { // rows the filter could not prove: exact scan, one CTA per row (rare)
       LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_exact_kernel<<<static_cast<unsigned>(rows), 256, E * 4 + 256 * k * 8, s>>>(q, t.inv_q, t.table, t.inv_t, t.N, E, k, t.flag, 0,
-                                                                                     nullptr, oi, os); }
-    PBG_CUDA(c, cudaGetLastError());
+      PBG_CUDA(c, launch_pdl(true, topk_exact_kernel, static_cast<unsigned>(std::min<long long>(rows, 2ll * c->num_sms)), 256,
+                             static_cast<size_t>(E * 4 + 256 * k * 8), s, q, t.inv_q, t.table, t.inv_t, t.N, E, k, t.flag, 0, nullptr, oi, os, rows)); }
   }
   return PBG_OK;
 }

@@ -87,6 +87,14 @@ struct TkSmem {
 };
 static_assert(TkSmem::kTotal <= 232448, "topk: shared memory budget");
 
+// Programmatic dependent launch along the chain prepare -> sample -> cut-off -> scan -> rescore -> exact scan (pbg.cu says
+// which links use it): a kernel releases its successor when it is done with its own work (released at entry, the
+// successor's CTAs sat in griddepcontrol.wait beside this kernel's and slowed it), and EVERY thread of every kernel
+// waits for its predecessor -- all of it, memory included -- before it touches anything the chain produced; a CTA that
+// skipped the wait could let its grid finish, and release the grid after it, too early.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------ 1. prepare
 // One warp per row: inv = 1 / max(||x||, 1e-12) (F.normalize's eps), bf16(x * inv) into a [rows_pad, E] matrix whose
 // padding rows are zero.  HBM-bound (E fp32 in, E bf16 + 4 B out per row): a warp takes R rows per iteration, every
@@ -96,6 +104,7 @@ static_assert(TkSmem::kTotal <= 232448, "topk: shared memory budget");
 template <int R, int V>
 __global__ void __launch_bounds__(256) topk_prepare_kernel(const float* __restrict__ x, long long rows, long long rows_pad, int E,
                                                            __nv_bfloat16* __restrict__ xn, float* __restrict__ inv) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarp = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(256) topk_prepare_kernel(const float* __restri
       }
     }
   }
+  pdl_launch_dependents();   // at the END: successors released at entry sit beside this kernel's blocks and slow them
 }
 
 // ------------------------------------------------------------------------------------------------ 2 / 3. sample, scan
@@ -202,6 +212,7 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lead_tmem_empty = mapa_u32(smem_u32(tmem_empty), 0);
+  pdl_wait();   // the prologue above touched nothing of the chain; the queries, the cut-offs, the lists do
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs, their halves)
@@ -360,6 +371,9 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
       }
     }
   }
+  // the successor (cut-off / rescoring kernel) may start now, while this CTA tears down: released at entry its CTAs sat
+  // in griddepcontrol.wait beside this kernel's for its whole length and slowed it (k = 64, B = 1024: 214 against 170 us)
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -377,6 +391,7 @@ pbg_topk_scan_kernel(const __grid_constant__ TopkParams p) {
 // candidates per row than a cut-off at s_k itself.  Fewer than k positive keys: tau = 0.
 __global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ samp_keys, int n_lists, long long B, long long rows_pad,
                                                        int k, float* __restrict__ tau) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows_pad) return;
@@ -402,6 +417,7 @@ __global__ void __launch_bounds__(256) topk_tau_kernel(const int* __restrict__ s
     kth = wbest;
   }
   if (lane == 0) tau[row] = kth > 0 ? fmaxf(__int_as_float(kth & ~0x1F) - (2.f * kTkErrBound + 1e-4f), 0.f) : 0.f;
+  pdl_launch_dependents();   // (an exited thread counts as well)
 }
 
 // ------------------------------------------------------------------------------------------------ 4. rescore
@@ -419,6 +435,9 @@ __global__ void __launch_bounds__(32 * kTkRescoreWarps) topk_rescore_kernel(cons
                                                            int* __restrict__ flag) {
   __shared__ float es_s[kTkRescoreWarps][kTkRescoreMax];
   __shared__ int ei_s[kTkRescoreWarps][kTkRescoreMax];
+  // (no early launch of the successor here: the exact-scan CTAs carry up to 131 KB of shared memory each and, parked on
+  // an SM, would take the room of four of this kernel's CTAs -- k = 64 ran 25 % slower that way)
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* es = es_s[w]; int* ei = ei_s[w];
   const long long row = static_cast<long long>(blockIdx.x) * kTkRescoreWarps + w;
@@ -529,10 +548,14 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
                                                          const float* __restrict__ table, const float* __restrict__ inv_t, long long N,
                                                          int E, int k, const int* __restrict__ flag, int always,
                                                          const float* __restrict__ raw, long long* __restrict__ out_idx,
-                                                         float* __restrict__ out_score) {
+                                                         float* __restrict__ out_score, long long n_rows) {
   extern __shared__ uint8_t sm[];
-  const long long row = blockIdx.x;
-  if (!always && flag[row] == 0) return;
+  pdl_launch_dependents();
+  pdl_wait();
+  // a CTA takes rows blockIdx.x, blockIdx.x + gridDim.x, ...: after the filter path nearly every row is proven and the
+  // launch is a few hundred CTAs that read their rows' flags and leave
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+  if (!always && flag[row] == 0) continue;
   const int nt = blockDim.x;
   float* qn = reinterpret_cast<float*>(sm);                 // [E]
   float* ms = qn + E;                                       // [nt * k] kept candidates
@@ -595,6 +618,7 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
     }
     __syncthreads();
   }
+  }   // rows of this CTA
 }
 
 }  // namespace pbg
