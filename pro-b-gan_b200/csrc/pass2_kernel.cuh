@@ -9,8 +9,8 @@
 // (M = 256: 128 rows of A per CTA; the BLOCK_N rows of W are split in halves, one per CTA), so a 64-deep k-block
 // costs each SM 16 KB of A + 16 KB of W (64 B/clk at full MMA rate) instead of 48 KB (96 B/clk) for a single-CTA
 // 128 x 256 tile, against ~70 B/clk/SM that the L2 fabric delivers chip-wide (profiles/ubench_r1_*.txt).  This main
-// loop alone sustains 546 clk per k-block on all 148 SMs with constant operands (floor 512; tools/ubench_pipe.cu); with real
-// operands and the rest of the chip busy it runs at ~756, the rate of the measured cuBLAS burst peak.
+// loop alone sustains 513-546 clk per k-block on all 148 SMs (floor 512; tools/ubench_pipe.cu); inside this kernel the
+// K = 1024 tiles run at 555-590 in a lone 48-SM pass and 595-660 with 148 SMs busy (-DPBG_KB_PROBE=1).
 //
 //   leader CTA (cluster rank 0)                               peer CTA (rank 1)
 //   warps 0..7  epilogue of its 128 rows / gather groups      warps 0..7  epilogue of its 128 rows / gather groups
