@@ -683,7 +683,8 @@ def run_b200(args, cfg: dict, rank: int, local_rank: int, world: int) -> None:
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         tj = json.loads(tf.read_text())
-        traffic = tj.get(f"{dom}_{args.config}", tj.get(dom) if args.config == "base" else None)
+        mode = "stage2" if args.stage_ahead == 2 else "fused"
+        traffic = tj.get(f"{dom}_{args.config}", tj.get(f"{dom}_{mode}", tj.get(dom)) if args.config == "base" else None)
         traffic_src = tj.get("source")
     roofline = {"bound": "tensor", "kernel": dom, "achieved": step_tflops, "peak": peak, "unit": "TFLOP/s",
                 "frac": step_tflops / peak, "traffic": traffic, "traffic_source": traffic_src,

@@ -114,6 +114,9 @@ struct alignas(64) Pass2Params {
   int no_deps;           // 1: single-layer launch (pbg_linear_bf16): the A operand is the caller's, nothing to wait for
   int discard;           // 1: dead workspace row blocks (activations and gathered rows the next layer has consumed) are
                          //    dropped from L2 with discard.global.L2 instead of being written back to HBM when evicted
+  const void* dead_xg;   // discard: the first-layer operand buffers of THIS pass when nothing will read them again (the
+  const void* dead_xd;   //    ctx's own gather buffers, or the staging slot a stage-next pass consumes), else null
+  int dead_ldg, dead_ldd;
   int poll_ns;
   int phase0_groups;    // 4-row gather groups (every row of the pass), done by the epilogue warps before their first tile
   int n_total;          // tickets of this launch
@@ -625,7 +628,6 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
     long long w_acc = 0, busy = 0, ph_wr = 0, ph_ld = 0, ph_math = 0, ph_st = 0, ph_n = 0, ph_m1 = 0, ph_w2 = 0;
     int item_no = 0;
     const int row_in_blk = static_cast<int>(rank) * 128 + q * 32 + lane;   // this thread's row within the 256-row block
-    const bool own_gather = p.phase0_groups > 0 && !p.gather_ahead && !p.gather_external;  // xg0 / xd0 were gathered by this launch, for this launch
     // The gather: 4-row groups claimed from a counter (claimed, not statically assigned: like the tickets, nothing may
     // depend on CTAs of this launch that are not resident yet -- several launches may share the device, and whatever
     // subset of a launch's CTAs is running has to be able to finish the pass on its own).  A warp gathers whenever it
@@ -816,10 +818,10 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           if (tr && threadIdx.x == kTraceThread) { pf_total += clock64() - t0; pf_n += 1; }
         }
         // G layer 1, first tile of the row block: every G L0 tile of the block has been published, so the block's gathered
-        // rows (written by this launch's gather) are dead
-        if (p.discard && kind == IT_G_L1 && n_blk == 0 && own_gather && p.gather.xg != nullptr)
-          p2_discard(static_cast<const char*>(p.gather.xg) + static_cast<size_t>(rb) * kP2Rows * p.gather.ldg * 2,
-                     static_cast<size_t>(kP2Rows) * p.gather.ldg * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
+        // rows are dead (when they are this pass's to drop: dead_xg)
+        if (p.discard && kind == IT_G_L1 && n_blk == 0 && p.dead_xg != nullptr)
+          p2_discard(static_cast<const char*>(p.dead_xg) + static_cast<size_t>(rb) * kP2Rows * p.dead_ldg * 2,
+                     static_cast<size_t>(kP2Rows) * p.dead_ldg * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
       } else if (ly.epi == PEPI_ROWDOT) {
         // ---- bias + LeakyReLU, dotted with the final [H/2 -> 1] weight; one partial per 64 columns, summed in a
         //      fixed order by the last warp to arrive for this row block
@@ -854,9 +856,9 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
           if (lane == 0) mbar_arrive_remote(lead_tmem_empty + acc * 8);
         }
         // first tile of the row block: every D L0 tile of the block has been published -> its gathered rows are dead
-        if (p.discard && n_blk == 0 && own_gather && p.gather.xd != nullptr)
-          p2_discard(static_cast<const char*>(p.gather.xd) + static_cast<size_t>(rb) * kP2Rows * p.gather.ldd * 2,
-                     static_cast<size_t>(kP2Rows) * p.gather.ldd * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
+        if (p.discard && n_blk == 0 && p.dead_xd != nullptr)
+          p2_discard(static_cast<const char*>(p.dead_xd) + static_cast<size_t>(rb) * kP2Rows * p.dead_ldd * 2,
+                     static_cast<size_t>(kP2Rows) * p.dead_ldd * 2, static_cast<int>(rank) * kP2Epi + wep, kP2WarpsPerPair, lane);
         const int old = warp_publish_fetch(p.fin + FIN_D * p.rb_cap + rb, lane);
         if (old == ly.n_tiles * kP2WarpsPerPair - 1) {
           fence_acq_rel_gpu();

@@ -521,6 +521,14 @@ int launch_pass2(pbg_ctx* c, Workspace& w, const Pass& a, const GatherParams& gp
   // in rotation over six lanes' workspaces: 31.9 -> 1.9 MB of DRAM writes per 4096-triplet launch,
   // profiles/dram_steady_r2.txt)
   p.discard = c->discard;
+  // the first-layer operand rows are this pass's to drop when it gathered them itself into the ctx's own buffers, or when
+  // it consumes a staging slot (pbg_score_staged_stage_next); a slot scored by pbg_score_staged may be scored again
+  if (!external_gather) {
+    p.dead_xg = gp.xg; p.dead_xd = gp.xd;
+  } else if (gather_ahead && slot) {
+    p.dead_xg = a.run_g ? slot->xg0 : nullptr; p.dead_xd = a.run_d ? slot->xd0 : nullptr;
+  }
+  p.dead_ldg = c->kg0p; p.dead_ldd = c->kd0p;
   p.nrb = nrb; p.rb_cap = w.mb_cap; p.M = static_cast<int>(rows); p.slope = c->dims.leaky_slope;
   p.sched = w.sched; p.ready = w.ready; p.fin = w.fin;
   p.gen_out = gen_out; p.out_f32 = a.out_dtype == PBG_DT_F32; p.n_valid = c->dims.embed_dim; p.ld_gen = c->dims.embed_dim;
@@ -1164,6 +1172,7 @@ int pbg_score_staged_stage_next(pbg_ctx* c, int slot, void* gen_out, int out_dty
   gp.xd = a.run_d ? nx.xd0 : nullptr; gp.ldd = c->kd0p;
   gp.B = next_B; gp.err_flag = c->err_flag;
   PBG_TRY(launch_pass2(c, c->ws_bf16, a, gp, 0, st.B, gen_out, gen_scores, true, &st, true));
+  if (c->discard) st.B = -1;   // consumed: its rows are dropped from L2 as the first layers finish with them
   nx.B = next_B; nx.has_g = a.run_g; nx.has_d = a.run_d; nx.has_xt = false;
   nx.node_emb = node_emb; nx.N = N; nx.tails = t + 2;
   return PBG_OK;

@@ -1,6 +1,6 @@
 """DRAM traffic of the pass in rotation (the command ncu wraps):
     ncu --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file X.csv \
-        python tools/dram_steady.py [LANES=6] [ROUNDS=8] [B=4096]
+        python tools/dram_steady.py [LANES=6] [ROUNDS=8] [B=4096] [stage2]
 LANES engines (one workspace each, like bench.py's lanes) take turns over distinct input batches.  A single cold launch
 shows 10 MB of DRAM traffic (inputs, outputs, cold weights: profiles/ncu_pass2_*.txt) because its dirty activation lines
 are still in L2 when it ends; in rotation the lanes' workspaces (6 x 30 MB) push each other's dead activations out of
@@ -39,12 +39,21 @@ node_emb, rel_w = (t.to(dev) for t in synth.make_tables())
 batches = [(synth.make_triplets(B, seed=100 + i).to(dev), synth.make_latents(B, seed=200 + i).to(dev)) for i in range(2 * LANES)]
 outs = [{"gen_out": torch.empty(B, 128, dtype=torch.bfloat16, device=dev), "gen_scores": torch.empty(B, device=dev),
          "logits": torch.empty(B, device=dev), "probs": torch.empty(B, device=dev)} for _ in range(LANES)]
+STAGE2 = len(sys.argv) > 4 and sys.argv[4] == "stage2"   # bench.py's default: every pass gathers the lane's next request
+kw = dict(want_gen_out=True, want_gen_scores=True, want_disc=True, out_dtype=torch.bfloat16)
 n = 0
+if STAGE2:
+    for l in range(LANES):
+        engs[l].reserve(B, "bf16", 2)
+        engs[l].stage_triplets(0, node_emb, rel_w, *batches[l % len(batches)])
 for r in range(ROUNDS):
     for l in range(LANES):
-        trip, z = batches[n % len(batches)]; n += 1
-        engs[l].score_triplets(node_emb, rel_w, trip, z, want_gen_out=True, want_gen_scores=True, want_disc=True,
-                               precision="bf16", out_dtype=torch.bfloat16, out=outs[l])
+        if STAGE2:
+            nxt = batches[(n + LANES) % len(batches)]; n += 1
+            engs[l].score_staged(r & 1, out=outs[l], stage_next=(node_emb, rel_w, *nxt), **kw)
+        else:
+            trip, z = batches[n % len(batches)]; n += 1
+            engs[l].score_triplets(node_emb, rel_w, trip, z, precision="bf16", out=outs[l], **kw)
 torch.cuda.synchronize()
 for e in engs:
     e.check_indices()
