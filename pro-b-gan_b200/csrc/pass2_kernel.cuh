@@ -293,9 +293,11 @@ __device__ __forceinline__ void p2_tail_dot(const uint8_t* st, const float* f, i
 // not waited for: the caller completes it (wait_group 0, then the arrival) -- `before_staging()` is called once this
 // group's row loads are in flight and before the staging tile is written, which is where the caller completes the
 // PREVIOUS group, so that a store's completion latency hides behind the next group's load latency.
+// keep: the rows are for a LATER launch (the next request of a stage-next pass): they are stored with the evict-last L2
+// policy, so that the traffic of the passes in between does not push them out to HBM and back.
 template <class F>
 __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long long group, int lane, uint8_t* st,
-                                                     F&& before_staging) {
+                                                     F&& before_staging, bool keep) {
   const long long r0 = group * 4;
   __nv_bfloat16* xg = static_cast<__nv_bfloat16*>(g.xg);
   __nv_bfloat16* xd = static_cast<__nv_bfloat16*>(g.xd);
@@ -351,7 +353,8 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && nrow > 0) {
-      bulk_store_1d(xg + r0 * wg, st, static_cast<uint32_t>(nrow * wg * 2));
+      if (keep) bulk_store_1d_hint(xg + r0 * wg, st, static_cast<uint32_t>(nrow * wg * 2), kEvictLast);
+      else bulk_store_1d(xg + r0 * wg, st, static_cast<uint32_t>(nrow * wg * 2));
       tma_store_commit();
       if (xd != nullptr) tma_store_wait_read<0>();
     }
@@ -368,7 +371,8 @@ __device__ __forceinline__ void p2_gather_group_bulk(const GatherParams& g, long
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && nrow > 0) {
-      bulk_store_1d(xd + r0 * wd, st, static_cast<uint32_t>(nrow * wd * 2));
+      if (keep) bulk_store_1d_hint(xd + r0 * wd, st, static_cast<uint32_t>(nrow * wd * 2), kEvictLast);
+      else bulk_store_1d(xd + r0 * wd, st, static_cast<uint32_t>(nrow * wd * 2));
       tma_store_commit();
     }
   }
@@ -649,7 +653,7 @@ pbg_pass2_kernel(const __grid_constant__ Pass2Params p) {
       if (g >= p.phase0_groups) { more_groups = false; return; }
       if (tr && threadIdx.x == kTraceThread) tr[249] = clock64();
       if (FASTG) {
-        p2_gather_group_bulk(p.gather, g, lane, st, gather_flush);
+        p2_gather_group_bulk(p.gather, g, lane, st, gather_flush, p.gather_ahead != 0);
         if (tr && threadIdx.x == kTraceThread) tr[250] = clock64();
         pend_rb = static_cast<int>(g / kP2GroupsPerBlock);   // completed by the next group, or by gather_flush()
         if (!p.gather_defer) gather_flush();                 // PBG_GATHER_DEFER=0: complete every group at once

@@ -175,6 +175,11 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// ... with an L2 cache policy for the written lines (kEvictLast: rows that wait in L2 for a later launch)
+__device__ __forceinline__ void bulk_store_1d_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t hint) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(hint) : "memory");
+}
 // 2-D tiled store smem -> global (bulk async group).
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
