@@ -267,7 +267,8 @@ int pbg_set_result_multicast(pbg_ctx* ctx, void* gen_out_mc, float* gen_scores_m
  * the prepared table.  E == 128, k <= 64 and N >= max(4096, 64 k x the sampling stride: 8 / 4 / 2 for k <= 16 / 32 / 64): bf16 tensor-core scores of a table sample give a cut-off per row, a second
  * tensor-core pass over the whole table marks every entity above it, every marked entity is re-scored exactly in fp32
  * and a row whose k-th exact score does not provably beat everything that was not marked is redone by an exact scan.
- * Other shapes (k up to 512, any E): exact fp32 scores by a SIMT GEMM over chunks of rows + one selection CTA per row.
+ * Other shapes (k up to 512, any E): exact fp32 scores by a SIMT GEMM over chunks of rows + one selection CTA per row
+ * (histogram of the row's scores, collect what lies at or above the k-th best's bin, sort).
  * Either way indices / scores are those of an fp32 evaluation (ties between equal scores: lower index first).
  * out_idx int64 [B, k], out_scores fp32 [B, k]; 1 <= k <= min(N, 512) (larger k: PBG_ERR_UNSUPPORTED).  Stream-ordered. */
 int pbg_topk_prepare(pbg_ctx* ctx, const float* table, int64_t N, void* stream);

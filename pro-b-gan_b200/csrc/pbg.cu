@@ -715,9 +715,15 @@ int topk_general(pbg_ctx* c, TopkState& t, const float* q, long long rows, int k
     { LaunchScope ls(c, PBG_K_OTHER, s);
       gemm_f32_kernel<ACT_NONE><<<grid, 256, 0, s>>>(gp); }
     PBG_CUDA(c, cudaGetLastError());
+    // selection: histogram + sort per row (topk_select_kernel); a row it cannot take (thousands of equal scores at the
+    // cut) is flagged and redone by the per-thread-list kernel
     { LaunchScope ls(c, PBG_K_OTHER, s);
-      topk_exact_kernel<<<static_cast<unsigned>(r), threads, smem, s>>>(q + off * E, t.inv_q + off, t.table, t.inv_t, t.N, E, k,
-                                                                        nullptr, 1, t.score_buf, oi + off * k, os + off * k, r); }
+      topk_select_kernel<<<static_cast<unsigned>(std::min<long long>(r, 6ll * c->num_sms)), kSelThreads, 0, s>>>(
+          t.score_buf, t.inv_q + off, t.inv_t, t.N, k, r, oi + off * k, os + off * k, t.flag + off); }
+    PBG_CUDA(c, cudaGetLastError());
+    { LaunchScope ls(c, PBG_K_OTHER, s);
+      topk_exact_kernel<<<static_cast<unsigned>(std::min<long long>(r, 2ll * c->num_sms)), threads, smem, s>>>(
+          q + off * E, t.inv_q + off, t.table, t.inv_t, t.N, E, k, t.flag + off, 0, t.score_buf, oi + off * k, os + off * k, r); }
     PBG_CUDA(c, cudaGetLastError());
   }
   return PBG_OK;

@@ -22,7 +22,7 @@
 //                by an exact scan of the table (rare).
 // so the returned indices are those of an exact fp32 evaluation, not of the bf16 scores.
 // Other shapes (k > 64, E != 128, small tables): exact fp32 scores of a chunk of rows by the SIMT GEMM of the parity
-// mode, then one selection CTA per row (pbg.cu: topk_general).
+// mode, then one selection CTA per row (topk_select_kernel below; pbg.cu: topk_general).
 #pragma once
 #include <cuda.h>
 #include "ptx.cuh"
@@ -540,6 +540,135 @@ __global__ void __launch_bounds__(32 * kTkRescoreWarps) topk_rescore_kernel(cons
   if (lane == 0) flag[row] = (kth > tau[row] + kTkErrBound) ? 0 : 4;
 }
 
+// ------------------------------------------------------------------------------------------------ general path: select
+// The k best of a row of exact scores [N] (general path: the fp32 GEMM's raw dot products, the row norms applied here),
+// for any k <= 512, without a per-thread candidate list: a 4096-bin histogram of the scores (cosines: linear bins over
+// [-1, 1]) gives the bin T that holds the k-th best; everything in the bins above it and in T itself -- k + a handful of
+// entries -- is collected into shared memory and sorted (bitonic, score descending, ties: lower index first).  A crowded
+// bin T (scores closer together than 5e-4) is split once more into 4096 sub-bins (1.2e-7 wide); a row that still does not
+// fit the 2048-entry buffer -- thousands of identical scores -- is flagged and left to topk_exact_kernel.  Two or three
+// coalesced reads of the row instead of O(k) shared-memory work per entity: k = 100 at B = 4096 took 31 ms in
+// topk_exact_kernel (k = 512 at B = 256: 51 ms).
+constexpr int kSelBins = 4096, kSelCap = 2048, kSelThreads = 256;
+// The three passes over a row must put every score into the SAME bin each time: the arithmetic is spelled with the
+// round-to-nearest intrinsics, which the compiler never contracts into an FMA (with `(r * iq * it + 1) * 2048` it fused the
+// last product into the add in one loop and not in another: one entry counted and not collected).
+__device__ __forceinline__ float tk_score(float raw, float iq, float it) { return __fmul_rn(__fmul_rn(raw, iq), it); }
+__device__ __forceinline__ int tk_bin(float s, float& x) {
+  x = __fmul_rn(__fadd_rn(s, 1.f), static_cast<float>(kSelBins / 2));
+  return min(kSelBins - 1, max(0, static_cast<int>(x)));
+}
+__device__ __forceinline__ int tk_subbin(float x, int b) {
+  return min(kSelBins - 1, max(0, static_cast<int>(__fmul_rn(__fsub_rn(x, static_cast<float>(b)), static_cast<float>(kSelBins)))));
+}
+// hist[] holds counts per bin; finds the largest bin t with count(bins >= t) >= need (need >= 1, total >= need):
+// *out_t = t, *out_above = count(bins > t).  All threads call; results valid after the trailing barrier.
+__device__ __forceinline__ void tk_find_bin(const unsigned* hist, int need, int* wsum, int* out_t, int* out_above) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int kPer = kSelBins / kSelThreads;            // 16 bins per thread, thread 0 owns the TOP bins
+  const int top = kSelBins - 1 - tid * kPer;
+  int local = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) local += static_cast<int>(hist[top - j]);
+  int incl = local;                                        // inclusive scan over threads (top-down)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int j = 0; j < w; ++j) base += wsum[j];
+  const int above = base + incl - local;                   // entries in bins above this thread's range
+  if (above < need && above + local >= need) {
+    int acc = above;
+    for (int j = 0; j < kPer; ++j) {
+      const int c = static_cast<int>(hist[top - j]);
+      if (acc + c >= need) { *out_t = top - j; *out_above = acc; break; }
+      acc += c;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const float* __restrict__ raw, const float* __restrict__ inv_q,
+                                                                  const float* __restrict__ inv_t, long long N, int k, long long n_rows,
+                                                                  long long* __restrict__ out_idx, float* __restrict__ out_score,
+                                                                  int* __restrict__ flag) {
+  __shared__ unsigned hist[kSelBins];
+  __shared__ float cs[kSelCap];
+  __shared__ int ci[kSelCap];
+  __shared__ int wsum[kSelThreads / 32];
+  __shared__ int s_t, s_above, s_t2, s_above2, s_cnt;
+  const int tid = threadIdx.x;
+  for (long long row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const float iq = inv_q[row];
+    const float* r = raw + row * N;
+    for (int b = tid; b < kSelBins; b += kSelThreads) hist[b] = 0u;
+    if (tid == 0) { s_cnt = 0; s_t2 = -1; s_above2 = 0; }
+    __syncthreads();
+    for (long long e = tid; e < N; e += kSelThreads) {
+      float x;
+      atomicAdd(&hist[tk_bin(tk_score(r[e], iq, inv_t[e]), x)], 1u);
+    }
+    __syncthreads();
+    tk_find_bin(hist, k, wsum, &s_t, &s_above);
+    const int T = s_t, above = s_above;
+    const bool crowded = above + static_cast<int>(hist[T]) > kSelCap;
+    __syncthreads();
+    if (crowded) {   // split bin T once more: the k - above best of ITS entries
+      for (int b = tid; b < kSelBins; b += kSelThreads) hist[b] = 0u;
+      __syncthreads();
+      for (long long e = tid; e < N; e += kSelThreads) {
+        float x;
+        const int b = tk_bin(tk_score(r[e], iq, inv_t[e]), x);
+        if (b == T) atomicAdd(&hist[tk_subbin(x, b)], 1u);
+      }
+      __syncthreads();
+      tk_find_bin(hist, k - above, wsum, &s_t2, &s_above2);
+    }
+    const int T2 = s_t2;
+    const int total = crowded ? above + s_above2 + static_cast<int>(hist[T2]) : above + static_cast<int>(hist[T]);
+    if (total > kSelCap) {     // (uniform) thousands of equal scores at the cut: the exact kernel takes the row
+      if (tid == 0) flag[row] = 1;
+      __syncthreads();
+      continue;
+    }
+    for (long long e = tid; e < N; e += kSelThreads) {
+      float x;
+      const float s = tk_score(r[e], iq, inv_t[e]);
+      const int b = tk_bin(s, x);
+      if (b > T || (b == T && (!crowded || tk_subbin(x, b) >= T2))) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        cs[pos] = s; ci[pos] = static_cast<int>(e);
+      }
+    }
+    __syncthreads();
+    int P = 1;
+    while (P < total) P <<= 1;
+    for (int i = min(total, s_cnt) + tid; i < P; i += kSelThreads) { cs[i] = -3.0e38f; ci[i] = 0x7fffffff; }   // s_cnt == total
+    __syncthreads();
+    // bitonic sort: score descending, equal scores by ascending index
+    for (int size = 2; size <= P; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = tid; i < (P >> 1); i += kSelThreads) {
+          const int lo = ((i / stride) * (stride << 1)) + (i % stride), hi = lo + stride;
+          const bool first_half = ((lo & size) == 0);      // this block of `size` sorts "best first"; the next one reversed
+          const float a = cs[lo], bq = cs[hi];
+          const int ai = ci[lo], bi = ci[hi];
+          const bool a_before_b = a > bq || (a == bq && ai < bi);
+          if (a_before_b != first_half) { cs[lo] = bq; cs[hi] = a; ci[lo] = bi; ci[hi] = ai; }
+        }
+        __syncthreads();
+      }
+    }
+    for (int j = tid; j < k; j += kSelThreads) {
+      out_idx[row * k + j] = j < total ? ci[j] : -1;
+      out_score[row * k + j] = j < total ? cs[j] : -3.0e38f;
+    }
+    if (tid == 0) flag[row] = 0;
+    __syncthreads();
+  }
+}
+
 // Exact selection, one CTA per row: every thread keeps the k best of its entities, the CTA merges (k rounds of a block
 // arg-max; ties: lower index first).  Two uses: rows whose flag is set after the filter path (always == 0; the scores
 // are computed here, fp32 SIMT over N x E -- slow by design, the proof fails rarely), and the general path
@@ -563,8 +692,10 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
   const float iq = inv_q[row];
   for (int c = threadIdx.x; c < E; c += nt) qn[c] = q[row * E + c] * iq;
   __syncthreads();
-  float* mys = ms + threadIdx.x * k; int* myi = mi + threadIdx.x * k;
-  for (int j = 0; j < k; ++j) { mys[j] = -3.0e38f; myi[j] = -1; }
+  // candidate j of thread t lives at [j * nt + t]: a warp's accesses to "its j-th candidates" hit 32 different banks
+  // (thread-major [t * k + j] is an 8-way bank conflict at k = 100 and made a 4096-row call 35 ms)
+  float* mys = ms + threadIdx.x; int* myi = mi + threadIdx.x;
+  for (int j = 0; j < k; ++j) { mys[j * nt] = -3.0e38f; myi[j * nt] = -1; }
   float tau = -3.0e38f;
   int filled = 0;
   for (long long e = threadIdx.x; e < N; e += nt) {
@@ -580,15 +711,16 @@ __global__ void __launch_bounds__(256) topk_exact_kernel(const float* __restrict
       }
     }
     if (filled < k) {              // the first k entities of a thread are simply kept
-      mys[filled] = d; myi[filled] = static_cast<int>(e); ++filled;
-      if (filled == k) { float mn = mys[0]; for (int j = 1; j < k; ++j) mn = fminf(mn, mys[j]); tau = mn; }
-    } else if (d > tau) {          // replace this thread's smallest
-      int at = 0; float mn = mys[0];
-      for (int j = 1; j < k; ++j) if (mys[j] < mn) { mn = mys[j]; at = j; }
-      mys[at] = d; myi[at] = static_cast<int>(e);
-      mn = mys[0];
-      for (int j = 1; j < k; ++j) mn = fminf(mn, mys[j]);
-      tau = mn;
+      mys[filled * nt] = d; myi[filled * nt] = static_cast<int>(e); ++filled;
+      if (filled == k) { float mn = mys[0]; for (int j = 1; j < k; ++j) mn = fminf(mn, mys[j * nt]); tau = mn; }
+    } else if (d > tau) {          // replace this thread's smallest; the new smallest comes out of the same scan
+      int at = 0; float mn = mys[0], mn2 = 3.0e38f;
+      for (int j = 1; j < k; ++j) {
+        const float v = mys[j * nt];
+        if (v < mn) { mn2 = mn; mn = v; at = j; } else mn2 = fminf(mn2, v);
+      }
+      mys[at * nt] = d; myi[at * nt] = static_cast<int>(e);
+      tau = fminf(mn2, d);
     }
   }
   __syncthreads();

@@ -71,6 +71,24 @@ def test_topk_k17_to_64_on_the_filter_path(dev):
     check(torch.randn(64, 128, generator=g), torch.randn(9000, 128, generator=g), 17, dev, min_exact=0.6)
 
 
+def test_topk_general_path_histogram_select_and_its_fallback(dev):
+    """The general path's selection (topk_select_kernel: 4096-bin histogram, collect, bitonic sort): large k, a crowded
+    threshold bin that needs the second histogram level (scores within 5e-4 of each other), and a row the kernel cannot
+    take -- thousands of IDENTICAL scores at the cut -- which must come back from the per-thread-list kernel with the
+    lowest indices first."""
+    import modular_prot_b_gan as m
+    g = torch.Generator().manual_seed(123)
+    check(torch.randn(70, 128, generator=g), torch.randn(3000, 128, generator=g), 300, dev, min_exact=0.0)
+    check(torch.randn(9, 128, generator=g), torch.randn(20000, 128, generator=g), 512, dev, min_exact=0.0)
+    base = torch.randn(1, 128, generator=g)
+    near = base + 2e-3 * torch.randn(6000, 128, generator=g)           # all cosines with `base` within ~1e-5 of each other
+    check(base + 0.05 * torch.randn(8, 128, generator=g), near, 70, dev, min_exact=0.0)
+    dup = torch.cat([base.repeat(3000, 1), torch.randn(500, 128, generator=g)])
+    s, i = m.cosine_topk(base.to(dev), dup.to(dev), 100)
+    assert torch.equal(i.cpu()[0], torch.arange(100)), "equal scores: lower index first"
+    assert (s.cpu() - 1.0).abs().max().item() < 1e-5
+
+
 def test_topk_k16_on_the_filter_path_and_ragged_sizes(dev):
     g = torch.Generator().manual_seed(21)
     check(torch.randn(1000, 128, generator=g), torch.randn(65536, 128, generator=g), 16, dev)

@@ -50,7 +50,7 @@ for B, N in ((4096, 65536), (256, 65536), (16, 65536), (16384, 65536)):
     print(f"B={B:6d} N={N}: fused {res['fused']:9.1f} us ({flop / res['fused'] / 1e6:7.1f} TFLOP/s, {B / res['fused']:.2f} M queries/s)   "
           f"torch lines on the same GPU {res['torch-on-gpu']:9.1f} us   x{res['torch-on-gpu'] / res['fused']:.1f}   {same}   rows sent to the exact scan: {flagged}   us per launch by kind {prof}", flush=True)
 
-# larger k: the filter path up to k = 64 (N >= 512 k), above that the general path (exact fp32 scores by the SIMT GEMM over row chunks + one selection CTA per row)
+# larger k: the filter path up to k = 64, above that the general path (exact fp32 scores by the SIMT GEMM over row chunks + histogram selection per row)
 for B, N, k2 in ((4096, 65536, 40), (256, 65536, 64), (4096, 65536, 100)):
     g = torch.Generator().manual_seed(B + N + k2)
     q, t = torch.randn(B, 128, generator=g).to(dev), torch.randn(N, 128, generator=g).to(dev)
