@@ -167,8 +167,8 @@ int pbg_score_staged(pbg_ctx* ctx, int slot, void* gen_out, int out_dtype, float
  * the table) must stay valid until IT has been scored (its cosine epilogue reads the tail rows through them).  A lane
  * of requests: pbg_stage_triplets(slot 0, first) once, then pbg_score_staged_stage_next(slot j & 1, ..., request j + 1)
  * per request and pbg_score_staged for the last.  The call CONSUMES the request staged in `slot` (with the workspace
- * discard on, its rows are dropped from L2 as the first layers finish with them): score it again only after staging it
- * again; pbg_score_staged leaves a slot intact. */
+ * discard on, its rows are dropped from L2 as the first layers finish with them): scoring the slot again before it
+ * has been staged again is refused (PBG_ERR_INVALID); pbg_score_staged leaves a slot intact. */
 int pbg_score_staged_stage_next(pbg_ctx* ctx, int slot, void* gen_out, int out_dtype, float* gen_scores, float* logits,
                                 float* probs, const float* node_emb, int64_t N, const float* rel_emb, int64_t R,
                                 const int64_t* next_triplets, const float* next_z, int64_t next_B, void* stream);

@@ -1178,7 +1178,7 @@ int pbg_score_staged_stage_next(pbg_ctx* c, int slot, void* gen_out, int out_dty
   gp.xd = a.run_d ? nx.xd0 : nullptr; gp.ldd = c->kd0p;
   gp.B = next_B; gp.err_flag = c->err_flag;
   PBG_TRY(launch_pass2(c, c->ws_bf16, a, gp, 0, st.B, gen_out, gen_scores, true, &st, true));
-  if (c->discard) st.B = -1;   // consumed: its rows are dropped from L2 as the first layers finish with them
+  st.B = -1;   // consumed (with the workspace discard on its rows are dropped from L2 as the first layers finish with them)
   nx.B = next_B; nx.has_g = a.run_g; nx.has_d = a.run_d; nx.has_xt = false;
   nx.node_emb = node_emb; nx.N = N; nx.tails = t + 2;
   return PBG_OK;

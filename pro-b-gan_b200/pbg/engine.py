@@ -353,7 +353,8 @@ class Engine:
         """The G + D pass over a staged request on the CURRENT stream (the compute stream); the caller has ordered it
         after the slot's stage_triplets.  Same result dict as score_triplets (bf16 mode).
         ``stage_next = (node_emb, rel_w, triplets, z)``: the same launch also stages that request into the other slot
-        (pbg_score_staged_stage_next) -- its tensors must stay alive until it has been scored."""
+        (pbg_score_staged_stage_next) -- its tensors must stay alive until it has been scored -- and CONSUMES `slot`:
+        stage it again before scoring it again."""
         res, out = {}, (out or {})
         B = getattr(self, "_staged_rows", {}).get(int(slot))
         if B is None:
@@ -393,6 +394,7 @@ class Engine:
                     self._h, int(slot), _ptr(gen_out), dt, _ptr(scores), _ptr(logits), _ptr(probs), _ptr(n_emb), n_emb.shape[0],
                     _ptr(n_rel), n_rel.shape[0], _ptr(n_trip), _ptr(n_z if run_g else None), n_trip.shape[0], self._stream()),
                     self._h)
+                self._staged_rows.pop(int(slot), None)            # consumed by this call (include/pbg.h)
                 self._staged_rows[1 - int(slot)] = n_trip.shape[0]
                 if not hasattr(self, "_staged_keep"):
                     self._staged_keep = {}

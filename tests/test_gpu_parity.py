@@ -549,6 +549,16 @@ def test_pass_that_stages_the_next_request_equals_the_fused_pass(cuda_models, de
         for j in range(len(inputs)):
             for k in ref[j]:
                 assert torch.equal(outs[j][k], ref[j][k]), f"graph, request {j}: {k} differs"
+    # the stage-next form consumes its slot: scoring it again without staging it again is refused
+    eng.stage_triplets(0, *dev_tables, *inputs[0])
+    eng.score_staged(0, stage_next=(*dev_tables, *inputs[1]), **kw)
+    with pytest.raises(Exception):
+        eng.score_staged(0, **kw)
+    eng.score_staged(1, **kw)            # the slot it staged is there, and a plain pbg_score_staged leaves it intact
+    again = eng.score_staged(1, **kw)
+    torch.cuda.synchronize()
+    for k_ in ref[1]:
+        assert torch.equal(again[k_], ref[1][k_]), f"slot scored twice: {k_} differs"
     # a bad id in the NEXT request is flagged by the pass that stages it
     bad = inputs[1][0].clone(); bad[3, 0] = 70000
     eng.stage_triplets(0, *dev_tables, *inputs[0])
