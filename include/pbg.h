@@ -264,7 +264,7 @@ int pbg_set_result_multicast(pbg_ctx* ctx, void* gen_out_mc, float* gen_scores_m
  *     top_scores, top_indices = similarities.topk(k, dim=1)                           (largest first)
  * pbg_topk_prepare reads the fp32 table [N, E] once (row norms + a normalised bf16 copy; the reference re-normalises
  * all N rows on every call) -- call it again whenever the table changes.  pbg_topk scores fp32 queries [B, E] against
- * the prepared table.  E == 128, k <= 64 and N >= max(4096, 64 k x the sampling stride: 8 / 4 / 2 for k <= 16 / 32 / 64): bf16 tensor-core scores of a table sample give a cut-off per row, a second
+ * the prepared table.  E == 128, k <= 64 and N >= max(4096, 64 k x the sampling stride: 4 for k <= 16, 2 above): bf16 tensor-core scores of a table sample give a cut-off per row, a second
  * tensor-core pass over the whole table marks every entity above it, every marked entity is re-scored exactly in fp32
  * and a row whose k-th exact score does not provably beat everything that was not marked is redone by an exact scan.
  * Other shapes (k up to 512, any E): exact fp32 scores by a SIMT GEMM over chunks of rows + one selection CTA per row

@@ -7,7 +7,7 @@
 // The [B, N] similarity matrix (1 GiB at B = 4096, N = 65536) never exists.  Steps (E = 128, k <= 16):
 //   1. prepare : row norms; bf16 copies of the normalised table / queries, zero padded to 256 rows        (HBM-bound)
 //   2. sample  : bf16 tensor-core scores (CTA pairs, tcgen05.mma.cta_group::2, M = 256 queries x N = 256 entities per
-//                MMA group, K = E = 128; query tile stationary, entity tiles streamed by TMA) of every 8th entity (k <= 16; every 4th / 2nd for k <= 32 / 64)
+//                MMA group, K = E = 128; query tile stationary, entity tiles streamed by TMA) of every 4th entity (k <= 16; every 2nd above)
 //                tile.  Epilogue per query row (one thread each): the maximum of every 32 scores as a packed
 //                (score | position) integer key -- one LOP3 per score and a three-input max tree -- pushed through a
 //                16-deep sorted insert once per 32 scores.  A small kernel merges a row's lists: tau[row] = the k-th
@@ -35,8 +35,11 @@ constexpr int kTkStages = 4;          // entity tiles in flight per CTA (32 KB e
 constexpr int kTkCand = 256;          // (group, mask) entries kept per (row, entity range, column half), in global memory
 constexpr int kTkMaxRanges = 16;
 constexpr int kTkMaxK = 64;           // largest k of the filter path; above it the general path runs
-// every stride-th 256-entity tile is sampled for the cut-off: 1 in 8 up to k = 16, 1 in 4 up to 32, 1 in 2 up to 64
-inline int tk_sample_stride(int k) { return k <= 16 ? 8 : (k <= 32 ? 4 : 2); }
+// every stride-th 256-entity tile is sampled for the cut-off.  About stride * k entities (+ those inside the error margin)
+// pass it and are rescored -- one 512-byte row read each, the largest part of a call -- while the sample launch costs
+// 1 / stride of the scan: measured at B = 4096, N = 65536: k = 10 156 / 141 / 141 us at 1 in 8 / 4 / 2, k = 17 172 / 163 us
+// and k = 40 267 / 238 us at 1 in 4 / 2
+inline int tk_sample_stride(int k) { return k <= 16 ? 4 : 2; }
 constexpr int kTkKeys = 16;           // best group keys a thread keeps per sample list; a row's lists together hold >= 2 k keys (pbg.cu: chunk size)
 constexpr int kTkRescoreMax = 1024;   // candidates per row the rescoring kernel takes (about 8 k + a dozen arrive); more: exact scan
 constexpr int kTkRescoreWarps = 4;    // rows per rescoring CTA (32 KB of candidate scores / indices in shared memory)
