@@ -3,10 +3,13 @@
 //
 // HBM layout per ctx (sized lazily to the largest batch chunk seen, <= kMaxChunk rows):
 //   weights   : fp32 [out,in] + bias (parity mode) and bf16 [out_p, in_p] zero-padded to the tile grid + padded bias
-//   bf16 mode : xg0 [rows, Kg0p]  xd0 [rows, Kd0p]  bufA [rows, Hmax]  bufB [rows, Hmax]   (bf16, K-major, the
-//               A operands of the next GEMM, each with a SWIZZLE_128B CUtensorMap of box 128 x 64)
-//   fp32 mode : the same four buffers in fp32
-// G: xg0 -> bufA -> bufB -> out.   D: xd0 -> bufA -> (logit, prob).   One stream at a time per ctx.
+//   bf16 mode : xg0 [rows, Kg0p]  xd0 [rows, Kd0p]  bufA [rows, Hmax]  bufB [rows, Hmax]  bufD [rows, Hdp]  (bf16,
+//               K-major, the A operands of the next GEMM, each with a SWIZZLE_128B CUtensorMap of box 128 x 64); two
+//               staging slots (xg0, xd0, fp32 tail rows) for requests gathered ahead of their pass
+//   fp32 mode : xg0, xd0, bufA, bufB in fp32
+// bf16 mode, one launch: G: xg0 -> bufA -> bufB -> out.   D: xd0 -> bufD -> (logit, prob); a row block of these buffers is
+// dropped from L2 (discard.global.L2) once its consumer layer is done with it.  fp32 mode, a launch per layer:
+// G: xg0 -> bufA -> bufB -> out.   D: xd0 -> bufA -> bufB -> (logit, prob).   One stream at a time per ctx.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
